@@ -1,0 +1,308 @@
+"""ctypes binding of libflinkms_b200.so -- the same C-ABI (include/flinkms.h) a JVM host binds through JNI.
+
+There is NO fallback: if the shared library is missing or no sm_100a GPU is present, loading / creating a
+context raises.  Nothing in this package imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflinkms_b200.so")
+
+OK = 0
+ERR_INVALID_ARG, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_OOM = -1, -2, -3, -4, -5
+X_DENSE_F32, X_DENSE_F64, X_CSR_F64 = 0, 1, 2
+RNG_PER_BLOCK, RNG_SHARED_SUBTASK = 0, 1
+USERS, ITEMS = 0, 1
+ALS_KERNEL_AUTO, ALS_KERNEL_GENERIC, ALS_KERNEL_TC = 0, 1, 2
+SVM_KERNEL_AUTO, SVM_KERNEL_GENERIC, SVM_KERNEL_WARP = 0, 1, 2
+
+_vp = C.c_void_p
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+
+# name -> (restype, argtypes); every symbol include/flinkms.h declares
+SIGNATURES = {
+    "fms_create": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int), C.c_int]),
+    "fms_destroy": (None, [_vp]),
+    "fms_last_error": (C.c_char_p, [_vp]),
+    "fms_version": (C.c_int, []),
+    "fms_stream": (_vp, [_vp]),
+    "fms_synchronize": (C.c_int, [_vp]),
+    "fms_launch_count": (C.c_int64, [_vp]),
+    "fms_als_fit": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int64, _i64p, _i64p]),
+    "fms_als_get_factors": (C.c_int, [_vp, C.c_int, _i64p, _f64p]),
+    "fms_als_set_model": (C.c_int, [_vp, _i64p, _f64p, C.c_int64, _i64p, _f64p, C.c_int64, C.c_int]),
+    "fms_als_predict": (C.c_int, [_vp, _i64p, _i64p, C.c_int64, _f64p, _u8p]),
+    "fms_als_mse": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64, _f64p, _i64p]),
+    "fms_als_load": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64, C.c_int, C.c_int, _i64p, _i64p]),
+    "fms_als_init": (C.c_int, [_vp, C.c_int, C.c_int64]),
+    "fms_als_half_step": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "fms_als_factors_device": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), _i64p, _i64p, _i64p]),
+    "fms_als_factors_updated": (C.c_int, [_vp, C.c_int]),
+    "fms_als_last_info": (C.c_int, [_vp, _i64p]),
+    "fms_als_set_kernel": (C.c_int, [_vp, C.c_int]),
+    "fms_svm_fit": (C.c_int, [_vp, _vp, C.c_int, _i64p, _i32p, _f64p, C.c_int64, C.c_int32, _i32p, C.c_int, C.c_int,
+                              C.c_int64, C.c_double, C.c_double, C.c_int64, C.c_int, _f64p]),
+    "fms_svm_predict": (C.c_int, [_vp, _vp, C.c_int, _i64p, _i32p, C.c_int64, C.c_int32, _f64p, C.c_double, C.c_int, _f64p]),
+    "fms_svm_set_weights": (C.c_int, [_vp, _f64p, C.c_int32]),
+    "fms_svm_get_weights": (C.c_int, [_vp, _f64p, C.c_int32]),
+    "fms_svm_get_alpha": (C.c_int, [_vp, _f64p, C.c_int64]),
+    "fms_svm_load": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _i64p, _i32p, _f64p, C.c_int64, C.c_int32, _i32p, C.c_int,
+                               C.c_int, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int]),
+    "fms_svm_sweep": (C.c_int, [_vp, C.c_int64]),
+    "fms_svm_delta_device": (C.c_int, [_vp, C.POINTER(_vp), _i32p]),
+    "fms_svm_apply_delta": (C.c_int, [_vp]),
+    "fms_svm_set_kernel": (C.c_int, [_vp, C.c_int]),
+    "fms_debug_index_stream": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int32, C.c_int64, _i32p]),
+}
+
+_lib = None
+
+
+class FlinkMSError(RuntimeError):
+    """What the JNI shim raises as a RuntimeException: non-zero status + fms_last_error."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"[fms status {status}] {message}")
+        self.status = status
+
+
+def load():
+    """dlopen the in-tree shared library and type every exported symbol.  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C flink-ms_b200).  There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the ABI and the header drift apart
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """One fms_ctx: one GPU, one stream.  Not thread-safe (like the reference's per-thread helpers)."""
+
+    def __init__(self, device: int | None = None):
+        self._lib = load()
+        self._h = _vp()
+        ids = None if device is None else (C.c_int * 1)(device)
+        rc = self._lib.fms_create(C.byref(self._h), ids, 1)
+        if rc != OK:
+            raise FlinkMSError(rc, (self._lib.fms_last_error(None) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fms_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != OK:
+            raise FlinkMSError(rc, (self._lib.fms_last_error(self._h) or b"").decode())
+
+    # ---- misc
+    @property
+    def stream(self) -> int:
+        return int(self._lib.fms_stream(self._h) or 0)
+
+    def synchronize(self):
+        self._check(self._lib.fms_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.fms_launch_count(self._h))
+
+    # ---- ALS
+    def als_fit(self, user, item, rating, rank, iterations, lam, seed):
+        u, i, r = _i64(user), _i64(item), _f64(rating)
+        if not (len(u) == len(i) == len(r)):
+            raise ValueError("user/item/rating lengths differ")
+        nu, ni = C.c_int64(), C.c_int64()
+        self._check(self._lib.fms_als_fit(self._h, _p(u, _i64p), _p(i, _i64p), _p(r, _f64p), len(u), rank, iterations,
+                                          lam, seed, C.byref(nu), C.byref(ni)))
+        self._als_shape = (nu.value, ni.value, rank)
+        return nu.value, ni.value
+
+    def als_load(self, user, item, rating, shard_index=0, shard_count=1):
+        u, i, r = _i64(user), _i64(item), _f64(rating)
+        nu, ni = C.c_int64(), C.c_int64()
+        self._check(self._lib.fms_als_load(self._h, _p(u, _i64p), _p(i, _i64p), _p(r, _f64p), len(u), shard_index,
+                                           shard_count, C.byref(nu), C.byref(ni)))
+        self._als_shape = (nu.value, ni.value, 0)
+        return nu.value, ni.value
+
+    def als_init(self, rank, seed):
+        self._check(self._lib.fms_als_init(self._h, rank, seed))
+        self._als_shape = (self._als_shape[0], self._als_shape[1], rank)
+
+    def als_half_step(self, which, lam):
+        self._check(self._lib.fms_als_half_step(self._h, which, lam))
+
+    def als_set_kernel(self, kernel):
+        self._check(self._lib.fms_als_set_kernel(self._h, kernel))
+
+    def als_last_info(self) -> int:
+        v = C.c_int64()
+        self._check(self._lib.fms_als_last_info(self._h, C.byref(v)))
+        return v.value
+
+    def als_factors_device(self, which):
+        ptr, rows, b, e = _vp(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self._lib.fms_als_factors_device(self._h, which, C.byref(ptr), C.byref(rows), C.byref(b), C.byref(e)))
+        return int(ptr.value or 0), rows.value, b.value, e.value
+
+    def als_factors_updated(self, which):
+        self._check(self._lib.fms_als_factors_updated(self._h, which))
+
+    def als_get_factors(self, which):
+        nu, ni, rank = self._als_shape
+        n = nu if which == USERS else ni
+        ids = np.empty(n, np.int64)
+        fac = np.empty((n, rank), np.float64)
+        self._check(self._lib.fms_als_get_factors(self._h, which, _p(ids, _i64p), _p(fac, _f64p)))
+        return ids, fac
+
+    def als_set_model(self, user_ids, user_factors, item_ids, item_factors):
+        ui, ii = _i64(user_ids), _i64(item_ids)
+        uf, itf = _f64(user_factors), _f64(item_factors)
+        rank = uf.shape[1] if uf.ndim == 2 and uf.shape[0] else (itf.shape[1] if itf.ndim == 2 else 0)
+        self._check(self._lib.fms_als_set_model(self._h, _p(ui, _i64p), _p(uf, _f64p), len(ui), _p(ii, _i64p),
+                                                _p(itf, _f64p), len(ii), rank))
+        self._als_shape = (len(ui), len(ii), rank)
+
+    def als_predict(self, u, i):
+        u, i = _i64(u), _i64(i)
+        if len(u) != len(i):
+            raise ValueError("u/i lengths differ")
+        out = np.empty(len(u), np.float64)
+        found = np.empty(len(u), np.uint8)
+        self._check(self._lib.fms_als_predict(self._h, _p(u, _i64p), _p(i, _i64p), len(u), _p(out, _f64p), _p(found, _u8p)))
+        return out, found.astype(bool)
+
+    def als_mse(self, u, i, rating):
+        u, i, r = _i64(u), _i64(i), _f64(rating)
+        mse, used = C.c_double(), C.c_int64()
+        self._check(self._lib.fms_als_mse(self._h, _p(u, _i64p), _p(i, _i64p), _p(r, _f64p), len(u), C.byref(mse), C.byref(used)))
+        return mse.value, used.value
+
+    # ---- SVM
+    @staticmethod
+    def _xargs(X, csr):
+        if csr is not None:
+            ptr, idx, val = csr
+            ptr = np.ascontiguousarray(ptr, np.int64)
+            idx = np.ascontiguousarray(idx, np.int32)
+            val = np.ascontiguousarray(val, np.float64)
+            return (ptr, idx, val), val.ctypes.data_as(_vp), X_CSR_F64, _p(ptr, _i64p), _p(idx, _i32p)
+        if isinstance(X, np.ndarray) and X.dtype == np.float32:
+            X = np.ascontiguousarray(X)
+            return (X,), X.ctypes.data_as(_vp), X_DENSE_F32, None, None
+        X = np.ascontiguousarray(X, np.float64)
+        return (X,), X.ctypes.data_as(_vp), X_DENSE_F64, None, None
+
+    def svm_fit(self, X, y, block_id, blocks, iterations, local_iterations, regularization=1.0, stepsize=1.0, seed=0,
+                rng_mode=RNG_PER_BLOCK, csr=None, dim=None):
+        keep, xp, dt, pp, ip = self._xargs(X, csr)
+        y = _f64(y)
+        dim = int(dim if dim is not None else X.shape[1])
+        b = np.ascontiguousarray(block_id, np.int32)
+        w = np.empty(dim, np.float64)
+        self._check(self._lib.fms_svm_fit(self._h, xp, dt, pp, ip, _p(y, _f64p), len(y), dim, _p(b, _i32p), blocks,
+                                          iterations, local_iterations, regularization, stepsize, seed, rng_mode, _p(w, _f64p)))
+        self._svm_n = len(y)
+        return w
+
+    def svm_load(self, X, y, block_id, blocks, shard_index=0, shard_count=1, regularization=1.0, stepsize=1.0, seed=0,
+                 rng_mode=RNG_PER_BLOCK, csr=None, dim=None, device_ptr=None, n=None):
+        """device_ptr: raw device address of a dense fp32 row-major X already on this ctx's GPU (used in place)."""
+        y = _f64(y)
+        b = np.ascontiguousarray(block_id, np.int32)
+        if device_ptr is not None:
+            xp, dt, pp, ip, isdev = _vp(device_ptr), X_DENSE_F32, None, None, 1
+            keep = ()
+        else:
+            keep, xp, dt, pp, ip = self._xargs(X, csr)
+            isdev = 0
+            dim = int(dim if dim is not None else X.shape[1])
+        self._check(self._lib.fms_svm_load(self._h, xp, dt, isdev, pp, ip, _p(y, _f64p), len(y), int(dim), _p(b, _i32p), blocks,
+                                           shard_index, shard_count, regularization, stepsize, seed, rng_mode))
+        self._svm_n = len(y)
+        self._svm_dim = int(dim)
+
+    def svm_sweep(self, local_iterations):
+        self._check(self._lib.fms_svm_sweep(self._h, local_iterations))
+
+    def svm_apply_delta(self):
+        self._check(self._lib.fms_svm_apply_delta(self._h))
+
+    def svm_delta_device(self):
+        ptr, dim = _vp(), C.c_int32()
+        self._check(self._lib.fms_svm_delta_device(self._h, C.byref(ptr), C.byref(dim)))
+        return int(ptr.value or 0), dim.value
+
+    def svm_set_kernel(self, kernel):
+        self._check(self._lib.fms_svm_set_kernel(self._h, kernel))
+
+    def svm_get_weights(self, dim):
+        w = np.empty(dim, np.float64)
+        self._check(self._lib.fms_svm_get_weights(self._h, _p(w, _f64p), dim))
+        return w
+
+    def svm_set_weights(self, w):
+        w = _f64(w)
+        self._check(self._lib.fms_svm_set_weights(self._h, _p(w, _f64p), len(w)))
+
+    def svm_get_alpha(self):
+        a = np.empty(self._svm_n, np.float64)
+        self._check(self._lib.fms_svm_get_alpha(self._h, _p(a, _f64p), self._svm_n))
+        return a
+
+    def svm_predict(self, X, w=None, threshold=0.0, output_decision_function=False, csr=None, dim=None, n=None):
+        keep, xp, dt, pp, ip = self._xargs(X, csr)
+        n = int(n if n is not None else (len(csr[0]) - 1 if csr is not None else X.shape[0]))
+        dim = int(dim if dim is not None else X.shape[1])
+        wv = None if w is None else _f64(w)
+        out = np.empty(n, np.float64)
+        self._check(self._lib.fms_svm_predict(self._h, xp, dt, pp, ip, n, dim, _p(wv, _f64p), threshold,
+                                              int(bool(output_decision_function)), _p(out, _f64p)))
+        return out
+
+    def debug_index_stream(self, seed, block, bound, count):
+        out = np.empty(count, np.int32)
+        self._check(self._lib.fms_debug_index_stream(self._h, seed, block, bound, count, _p(out, _i32p)))
+        return out

@@ -1,0 +1,582 @@
+// api.cu -- the C-ABI of include/flinkms.h: argument checking, host<->device staging, kernel sequencing.
+// No CPU fallback anywhere: every compute entry point needs the ctx's GPU.
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+
+using namespace fms;
+
+static thread_local std::string g_create_error;
+
+#define CHECK_CTX(ctx) \
+    do {               \
+        if (!(ctx)) return FMS_ERR_INVALID_ARG; \
+        cudaError_t e_ = cudaSetDevice((ctx)->device); \
+        if (e_ != cudaSuccess) return fail((ctx), FMS_ERR_CUDA, "cudaSetDevice(%d): %s", (ctx)->device, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" {
+
+FMS_API int fms_version(void) { return 100; }
+
+FMS_API int fms_create(fms_ctx **out, const int *device_ids, int n_devices) {
+    if (!out) return FMS_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (n_devices != 1) {
+        g_create_error = "fms_create: n_devices must be 1 (one process per GPU; shard with one ctx per rank)";
+        return FMS_ERR_UNSUPPORTED;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        g_create_error = std::string("fms_create: no CUDA device (") + cudaGetErrorString(e) + ") -- libflinkms_b200 has no CPU fallback";
+        cudaGetLastError();
+        return FMS_ERR_CUDA;
+    }
+    int dev = 0;
+    if (device_ids) dev = device_ids[0];
+    else if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    if (dev < 0 || dev >= count) {
+        g_create_error = "fms_create: device id out of range";
+        return FMS_ERR_INVALID_ARG;
+    }
+    if ((e = cudaSetDevice(dev)) != cudaSuccess) {
+        g_create_error = std::string("fms_create: cudaSetDevice: ") + cudaGetErrorString(e);
+        return FMS_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) {
+        g_create_error = std::string("fms_create: cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return FMS_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_error = "fms_create: libflinkms_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                         std::to_string(prop.minor);
+        return FMS_ERR_UNSUPPORTED;
+    }
+    fms_ctx *ctx = new (std::nothrow) fms_ctx();
+    if (!ctx) return FMS_ERR_OOM;
+    ctx->device = dev;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("fms_create: cudaStreamCreate: ") + cudaGetErrorString(e);
+        delete ctx;
+        return FMS_ERR_CUDA;
+    }
+    *out = ctx;
+    return FMS_OK;
+}
+
+FMS_API void fms_destroy(fms_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+FMS_API const char *fms_last_error(const fms_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+FMS_API void *fms_stream(fms_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+FMS_API int64_t fms_launch_count(const fms_ctx *ctx) { return ctx ? ctx->launches : 0; }
+FMS_API int fms_synchronize(fms_ctx *ctx) {
+    CHECK_CTX(ctx);
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
+// ====================================================================================================== ALS
+FMS_API int fms_als_load(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t nnz,
+                         int shard_index, int shard_count, int64_t *n_users, int64_t *n_items) {
+    CHECK_CTX(ctx);
+    if (nnz < 0 || (nnz > 0 && (!user || !item || !rating))) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_load: null input or nnz < 0");
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count)
+        return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_load: bad shard %d/%d", shard_index, shard_count);
+    if (nnz >= ((int64_t)1 << 31) * 8) return fail(ctx, FMS_ERR_UNSUPPORTED, "fms_als_load: nnz too large");
+    AlsState &A = ctx->als;
+    A.loaded = A.inited = false;
+    A.model_external = false;
+    FMS_TRY(als_build_csr(ctx, user, item, rating, nnz));
+    A.shard_index = shard_index;
+    A.shard_count = shard_count;
+    A.shard_rows[0] = (A.n_users + shard_count - 1) / shard_count;
+    A.shard_rows[1] = (A.n_items + shard_count - 1) / shard_count;
+    A.loaded = true;
+    if (n_users) *n_users = A.n_users;
+    if (n_items) *n_items = A.n_items;
+    return FMS_OK;
+}
+
+FMS_API int fms_als_init(fms_ctx *ctx, int rank, int64_t seed) {
+    CHECK_CTX(ctx);
+    AlsState &A = ctx->als;
+    if (!A.loaded) return fail(ctx, FMS_ERR_STATE, "fms_als_init: no ratings loaded");
+    if (rank < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_init: rank %d < 1", rank);
+    if (rank > 128) return fail(ctx, FMS_ERR_UNSUPPORTED, "fms_als_init: rank %d > 128 is not supported", rank);
+    A.rank = rank;
+    FMS_TRY(als_launch_init(ctx, seed));
+    A.inited = true;
+    return FMS_OK;
+}
+
+FMS_API int fms_als_set_kernel(fms_ctx *ctx, int kernel) {
+    if (!ctx) return FMS_ERR_INVALID_ARG;
+    if (kernel < FMS_ALS_KERNEL_AUTO || kernel > FMS_ALS_KERNEL_TC) return fail(ctx, FMS_ERR_INVALID_ARG, "bad ALS kernel id %d", kernel);
+    ctx->als.kernel = kernel;
+    return FMS_OK;
+}
+
+FMS_API int fms_als_half_step(fms_ctx *ctx, int which, double lambda) {
+    CHECK_CTX(ctx);
+    AlsState &A = ctx->als;
+    if (!A.loaded || !A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_half_step: load + init first");
+    if (which != FMS_USERS && which != FMS_ITEMS) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_half_step: which = %d", which);
+    const int64_t n = which == FMS_USERS ? A.n_users : A.n_items;
+    const int64_t rb = std::min<int64_t>(n, A.shard_rows[which] * A.shard_index);
+    const int64_t re = std::min<int64_t>(n, rb + A.shard_rows[which]);
+    FMS_CUDA(ctx, cudaMemsetAsync(A.info.p, 0, sizeof(int), ctx->stream));
+    bool tc = false;
+    if (A.kernel != FMS_ALS_KERNEL_GENERIC) tc = als_tc_supported(ctx, A.rank) != 0;
+    if (A.kernel == FMS_ALS_KERNEL_TC && !tc) return fail(ctx, FMS_ERR_UNSUPPORTED, "tensor-core ALS kernel does not cover rank %d", A.rank);
+    if (tc) FMS_TRY(als_launch_half_step_tc(ctx, which, (float)lambda, rb, re));
+    else FMS_TRY(als_launch_half_step_generic(ctx, which, (float)lambda, rb, re));
+    A.fac64_valid = false;
+    A.plane_valid[which] = false;
+    A.last_bad = -1;
+    return FMS_OK;
+}
+
+FMS_API int fms_als_last_info(fms_ctx *ctx, int64_t *bad_rows) {
+    CHECK_CTX(ctx);
+    AlsState &A = ctx->als;
+    if (!A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_last_info: no half-step run");
+    int h = 0;
+    FMS_CUDA(ctx, cudaMemcpyAsync(&h, A.info.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad_rows) *bad_rows = h;
+    return FMS_OK;
+}
+
+FMS_API int fms_als_factors_device(fms_ctx *ctx, int which, void **dev_ptr, int64_t *rows_padded, int64_t *shard_begin,
+                                   int64_t *shard_end) {
+    if (!ctx) return FMS_ERR_INVALID_ARG;
+    AlsState &A = ctx->als;
+    if (!A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_factors_device: init first");
+    if (which != 0 && which != 1) return fail(ctx, FMS_ERR_INVALID_ARG, "which = %d", which);
+    const int64_t n = which == 0 ? A.n_users : A.n_items;
+    if (dev_ptr) *dev_ptr = A.fac[which].p;
+    if (rows_padded) *rows_padded = A.shard_rows[which] * A.shard_count;
+    if (shard_begin) *shard_begin = std::min<int64_t>(n, A.shard_rows[which] * A.shard_index);
+    if (shard_end) *shard_end = std::min<int64_t>(n, A.shard_rows[which] * (A.shard_index + 1));
+    return FMS_OK;
+}
+
+FMS_API int fms_als_factors_updated(fms_ctx *ctx, int which) {
+    if (!ctx) return FMS_ERR_INVALID_ARG;
+    if (which != 0 && which != 1) return fail(ctx, FMS_ERR_INVALID_ARG, "which = %d", which);
+    ctx->als.fac64_valid = false;
+    ctx->als.plane_valid[which] = false;
+    return FMS_OK;
+}
+
+FMS_API int fms_als_fit(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t nnz, int rank,
+                        int iterations, double lambda, int64_t seed, int64_t *n_users, int64_t *n_items) {
+    CHECK_CTX(ctx);
+    if (iterations < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_fit: iterations %d < 0", iterations);
+    if (rank < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_fit: rank %d < 1", rank);
+    FMS_TRY(fms_als_load(ctx, user, item, rating, nnz, 0, 1, n_users, n_items));
+    FMS_TRY(fms_als_init(ctx, rank, seed));
+    for (int t = 0; t < iterations; ++t) {
+        FMS_TRY(fms_als_half_step(ctx, FMS_USERS, lambda));
+        FMS_TRY(fms_als_half_step(ctx, FMS_ITEMS, lambda));
+    }
+    FMS_TRY(fms_als_half_step(ctx, FMS_USERS, lambda));   // the extra user half-step after the loop
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
+FMS_API int fms_als_get_factors(fms_ctx *ctx, int which, int64_t *ids, double *factors) {
+    CHECK_CTX(ctx);
+    AlsState &A = ctx->als;
+    if (!A.inited && !A.model_external) return fail(ctx, FMS_ERR_STATE, "The ALS model has not been fitted.");
+    if (which != 0 && which != 1) return fail(ctx, FMS_ERR_INVALID_ARG, "which = %d", which);
+    const int64_t n = which == 0 ? A.n_users : A.n_items;
+    if (ids && n) FMS_CUDA(ctx, cudaMemcpyAsync(ids, A.ids[which].p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (factors && n) {
+        FMS_TRY(als_ensure_fac64(ctx));
+        FMS_CUDA(ctx, cudaMemcpyAsync(factors, A.fac64[which].p, (size_t)n * A.rank * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
+FMS_API int fms_als_set_model(fms_ctx *ctx, const int64_t *user_ids, const double *user_factors, int64_t n_users,
+                              const int64_t *item_ids, const double *item_factors, int64_t n_items, int rank) {
+    CHECK_CTX(ctx);
+    if (n_users < 0 || n_items < 0 || rank < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_set_model: bad sizes");
+    if ((n_users && (!user_ids || !user_factors)) || (n_items && (!item_ids || !item_factors)))
+        return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_set_model: null input");
+    for (int64_t k = 1; k < n_users; ++k) if (user_ids[k] <= user_ids[k - 1]) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_set_model: user ids must be strictly ascending");
+    for (int64_t k = 1; k < n_items; ++k) if (item_ids[k] <= item_ids[k - 1]) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_set_model: item ids must be strictly ascending");
+    AlsState &A = ctx->als;
+    A.loaded = A.inited = false;
+    A.rank = rank;
+    A.n_users = n_users;
+    A.n_items = n_items;
+    const int64_t n[2] = {n_users, n_items};
+    const int64_t *idp[2] = {user_ids, item_ids};
+    const double *fp[2] = {user_factors, item_factors};
+    for (int s = 0; s < 2; ++s) {
+        FMS_CUDA(ctx, A.ids[s].alloc((size_t)n[s]));
+        FMS_CUDA(ctx, A.fac64[s].alloc((size_t)n[s] * rank));
+        if (n[s]) {
+            FMS_CUDA(ctx, cudaMemcpyAsync(A.ids[s].p, idp[s], (size_t)n[s] * 8, cudaMemcpyHostToDevice, ctx->stream));
+            FMS_CUDA(ctx, cudaMemcpyAsync(A.fac64[s].p, fp[s], (size_t)n[s] * rank * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    A.fac64_valid = true;
+    A.model_external = true;
+    return FMS_OK;
+}
+
+__global__ void k_sq_err(const double *__restrict__ pred, const uint8_t *__restrict__ found, const double *__restrict__ rating,
+                         int64_t n, double *__restrict__ acc /* [0]=sum, [1]=count */) {
+    double s = 0.0, c = 0.0;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        if (found[k]) { const double e = rating[k] - pred[k]; s += e * e; c += 1.0; }
+    s = warp_sum(s);
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], s); atomicAdd(&acc[1], c); }
+}
+
+static int predict_common(fms_ctx *ctx, const int64_t *u, const int64_t *i, int64_t n, DevBuf<int64_t> &du, DevBuf<int64_t> &di,
+                          DevBuf<double> &dout, DevBuf<uint8_t> &dfound) {
+    AlsState &A = ctx->als;
+    if (!A.inited && !A.model_external) return fail(ctx, FMS_ERR_STATE, "The ALS model has not been fitted.");
+    if (n < 0 || (n && (!u || !i))) return fail(ctx, FMS_ERR_INVALID_ARG, "predict: null input or n < 0");
+    FMS_TRY(als_ensure_fac64(ctx));
+    FMS_CUDA(ctx, du.alloc((size_t)n));
+    FMS_CUDA(ctx, di.alloc((size_t)n));
+    FMS_CUDA(ctx, dout.alloc((size_t)n));
+    FMS_CUDA(ctx, dfound.alloc((size_t)n));
+    if (n) {
+        FMS_CUDA(ctx, cudaMemcpyAsync(du.p, u, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        FMS_CUDA(ctx, cudaMemcpyAsync(di.p, i, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return als_predict_device(ctx, du.p, di.p, n, dout.p, dfound.p);
+}
+
+FMS_API int fms_als_predict(fms_ctx *ctx, const int64_t *u, const int64_t *i, int64_t n, double *out, uint8_t *found) {
+    CHECK_CTX(ctx);
+    if (n && !out) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_predict: out is null");
+    DevBuf<int64_t> du, di;
+    DevBuf<double> dout;
+    DevBuf<uint8_t> dfound;
+    FMS_TRY(predict_common(ctx, u, i, n, du, di, dout, dfound));
+    if (n) {
+        FMS_CUDA(ctx, cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (found) FMS_CUDA(ctx, cudaMemcpyAsync(found, dfound.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
+FMS_API int fms_als_mse(fms_ctx *ctx, const int64_t *u, const int64_t *i, const double *rating, int64_t n, double *mse,
+                        int64_t *n_used) {
+    CHECK_CTX(ctx);
+    if (n && !rating) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_mse: rating is null");
+    DevBuf<int64_t> du, di;
+    DevBuf<double> dout, dr, acc;
+    DevBuf<uint8_t> dfound;
+    FMS_TRY(predict_common(ctx, u, i, n, du, di, dout, dfound));
+    FMS_CUDA(ctx, dr.alloc((size_t)n));
+    FMS_CUDA(ctx, acc.alloc(2));
+    FMS_CUDA(ctx, cudaMemsetAsync(acc.p, 0, 16, ctx->stream));
+    double h[2] = {0, 0};
+    if (n) {
+        FMS_CUDA(ctx, cudaMemcpyAsync(dr.p, rating, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        k_sq_err<<<(unsigned)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(dout.p, dfound.p, dr.p, n, acc.p);
+        FMS_LAUNCH_CHECK(ctx);
+        FMS_CUDA(ctx, cudaMemcpyAsync(h, acc.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (mse) *mse = h[1] > 0 ? h[0] / h[1] : 0.0;
+    if (n_used) *n_used = (int64_t)h[1];
+    return FMS_OK;
+}
+
+// ====================================================================================================== SVM
+__global__ void k_f64_to_f32_chunk(const double *__restrict__ in, int64_t n, float *__restrict__ out) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (float)in[k];
+}
+
+static int upload_f64_as_f32(fms_ctx *ctx, const double *h, int64_t n, float *d_out) {
+    const int64_t CH = (int64_t)1 << 24;   // 128 MB staging
+    DevBuf<double> stage;
+    FMS_CUDA(ctx, stage.alloc((size_t)std::min<int64_t>(n, CH)));
+    for (int64_t o = 0; o < n; o += CH) {
+        const int64_t c = std::min<int64_t>(CH, n - o);
+        FMS_CUDA(ctx, cudaMemcpyAsync(stage.p, h + o, (size_t)c * 8, cudaMemcpyHostToDevice, ctx->stream));
+        k_f64_to_f32_chunk<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(stage.p, c, d_out + o);
+        FMS_LAUNCH_CHECK(ctx);
+        FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return FMS_OK;
+}
+
+FMS_API int fms_svm_set_kernel(fms_ctx *ctx, int kernel) {
+    if (!ctx) return FMS_ERR_INVALID_ARG;
+    if (kernel < FMS_SVM_KERNEL_AUTO || kernel > FMS_SVM_KERNEL_WARP) return fail(ctx, FMS_ERR_INVALID_ARG, "bad SVM kernel id %d", kernel);
+    ctx->svm.kernel = kernel;
+    return FMS_OK;
+}
+
+FMS_API int fms_svm_load(fms_ctx *ctx, const void *X, int x_dtype, int X_is_device, const int64_t *csr_ptr, const int32_t *csr_idx,
+                         const double *y, int64_t n, int32_t dim, const int32_t *block_id, int blocks, int shard_index,
+                         int shard_count, double regularization, double stepsize, int64_t seed, int rng_mode) {
+    CHECK_CTX(ctx);
+    SvmState &S = ctx->svm;
+    S.loaded = false;
+    if (n < 0 || dim < 1 || blocks < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: n=%lld dim=%d blocks=%d", (long long)n, dim, blocks);
+    if (n > 0 && (!X || !y || !block_id)) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: null input");
+    if (x_dtype < FMS_X_DENSE_F32 || x_dtype > FMS_X_CSR_F64) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: x_dtype %d", x_dtype);
+    if (x_dtype == FMS_X_CSR_F64 && n > 0 && (!csr_ptr || !csr_idx)) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: CSR arrays missing");
+    if (X_is_device && x_dtype != FMS_X_DENSE_F32) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: device X must be dense fp32");
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: bad shard");
+    if (rng_mode != FMS_RNG_PER_BLOCK && rng_mode != FMS_RNG_SHARED_SUBTASK) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: rng_mode %d", rng_mode);
+    if (n >= ((int64_t)1 << 31)) return fail(ctx, FMS_ERR_UNSUPPORTED, "fms_svm_load: n >= 2^31 (Random.nextInt bound is an int)");
+    if (!(regularization > 0.0)) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: regularization must be > 0");
+    cudaStream_t st = ctx->stream;
+    S.n = n; S.dim = dim; S.blocks = blocks; S.shard_index = shard_index; S.shard_count = shard_count;
+    S.lambda = regularization; S.stepsize = stepsize; S.seed = seed; S.rng_mode = rng_mode;
+    // ---- group rows by block (arrival order inside a block)
+    std::vector<int64_t> cnt((size_t)blocks + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        if (block_id[i] < 0 || block_id[i] >= blocks) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: block_id[%lld]=%d out of range", (long long)i, block_id[i]);
+        cnt[(size_t)block_id[i] + 1]++;
+    }
+    for (int k = 0; k < blocks; ++k) cnt[(size_t)k + 1] += cnt[(size_t)k];
+    std::vector<int64_t> rows((size_t)n), fill(cnt.begin(), cnt.end() - 1);
+    for (int64_t i = 0; i < n; ++i) rows[(size_t)fill[(size_t)block_id[i]]++] = i;
+    S.h_blk_ptr = cnt;
+    FMS_CUDA(ctx, S.rows.alloc((size_t)n));
+    FMS_CUDA(ctx, S.blk_ptr.alloc((size_t)blocks + 1));
+    if (n) FMS_CUDA(ctx, cudaMemcpyAsync(S.rows.p, rows.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    FMS_CUDA(ctx, cudaMemcpyAsync(S.blk_ptr.p, cnt.data(), ((size_t)blocks + 1) * 8, cudaMemcpyHostToDevice, st));
+    S.local_blocks.clear();
+    for (int k = 0; k < blocks; ++k) if (k % shard_count == shard_index) S.local_blocks.push_back(k);
+    if (rng_mode == FMS_RNG_SHARED_SUBTASK) { S.local_blocks.clear(); for (int k = 0; k < blocks; ++k) S.local_blocks.push_back(k); }
+    const size_t n_local = S.local_blocks.size();
+    FMS_CUDA(ctx, S.d_local_blocks.alloc(n_local));
+    if (n_local) FMS_CUDA(ctx, cudaMemcpyAsync(S.d_local_blocks.p, S.local_blocks.data(), n_local * 4, cudaMemcpyHostToDevice, st));
+    std::vector<uint64_t> rng((size_t)blocks);
+    for (int k = 0; k < blocks; ++k) rng[(size_t)k] = JRand::scramble((long long)(seed ^ (int64_t)k));
+    FMS_CUDA(ctx, S.rng.alloc((size_t)blocks));
+    FMS_CUDA(ctx, cudaMemcpyAsync(S.rng.p, rng.data(), (size_t)blocks * 8, cudaMemcpyHostToDevice, st));
+    // ---- labels
+    FMS_CUDA(ctx, S.y.alloc((size_t)n));
+    if (n) FMS_TRY(upload_f64_as_f32(ctx, y, n, S.y.p));
+    // ---- design matrix
+    S.X = nullptr;
+    if (x_dtype == FMS_X_CSR_F64) {
+        S.x_kind = FMS_X_CSR_F64;
+        const int64_t nnz = n ? csr_ptr[n] : 0;
+        for (int64_t p = 0; p < nnz; ++p) if (csr_idx[p] < 0 || csr_idx[p] >= dim) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: csr_idx[%lld]=%d outside [0,%d)", (long long)p, csr_idx[p], dim);
+        FMS_CUDA(ctx, S.csr_ptr.alloc((size_t)n + 1));
+        FMS_CUDA(ctx, S.csr_idx.alloc((size_t)nnz));
+        FMS_CUDA(ctx, S.csr_val.alloc((size_t)nnz));
+        if (n) FMS_CUDA(ctx, cudaMemcpyAsync(S.csr_ptr.p, csr_ptr, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (nnz) {
+            FMS_CUDA(ctx, cudaMemcpyAsync(S.csr_idx.p, csr_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+            FMS_TRY(upload_f64_as_f32(ctx, (const double *)X, nnz, S.csr_val.p));
+        }
+        S.X_own.release();
+    } else {
+        S.x_kind = FMS_X_DENSE_F32;
+        const int64_t cnt_x = n * (int64_t)dim;
+        if (X_is_device) {
+            S.X = (const float *)X;
+            S.X_own.release();
+        } else {
+            FMS_CUDA(ctx, S.X_own.alloc((size_t)cnt_x));
+            if (cnt_x) {
+                if (x_dtype == FMS_X_DENSE_F32) FMS_CUDA(ctx, cudaMemcpyAsync(S.X_own.p, X, (size_t)cnt_x * 4, cudaMemcpyHostToDevice, st));
+                else FMS_TRY(upload_f64_as_f32(ctx, (const double *)X, cnt_x, S.X_own.p));
+            }
+            S.X = S.X_own.p;
+        }
+    }
+    // ---- state
+    FMS_CUDA(ctx, S.alpha.alloc((size_t)n));
+    FMS_CUDA(ctx, cudaMemsetAsync(S.alpha.p, 0, (size_t)std::max<int64_t>(n, 1) * 4, st));
+    FMS_CUDA(ctx, S.w.alloc((size_t)dim));
+    FMS_CUDA(ctx, cudaMemsetAsync(S.w.p, 0, (size_t)dim * 4, st));
+    FMS_CUDA(ctx, S.delta.alloc((size_t)dim));
+    FMS_CUDA(ctx, cudaMemsetAsync(S.delta.p, 0, (size_t)dim * 4, st));
+    FMS_CUDA(ctx, S.dw_blocks.alloc(std::max<size_t>(n_local, 1) * (size_t)dim));
+    FMS_CUDA(ctx, cudaStreamSynchronize(st));
+    S.w64_valid = false;
+    S.loaded = true;
+    return FMS_OK;
+}
+
+FMS_API int fms_svm_sweep(fms_ctx *ctx, int64_t local_iterations) {
+    CHECK_CTX(ctx);
+    if (!ctx->svm.loaded) return fail(ctx, FMS_ERR_STATE, "fms_svm_sweep: load first");
+    return svm_launch_sweep(ctx, local_iterations);
+}
+
+FMS_API int fms_svm_delta_device(fms_ctx *ctx, void **dev_ptr, int32_t *dim) {
+    if (!ctx) return FMS_ERR_INVALID_ARG;
+    if (!ctx->svm.loaded) return fail(ctx, FMS_ERR_STATE, "fms_svm_delta_device: load first");
+    if (dev_ptr) *dev_ptr = ctx->svm.delta.p;
+    if (dim) *dim = ctx->svm.dim;
+    return FMS_OK;
+}
+
+FMS_API int fms_svm_apply_delta(fms_ctx *ctx) {
+    CHECK_CTX(ctx);
+    if (!ctx->svm.loaded) return fail(ctx, FMS_ERR_STATE, "fms_svm_apply_delta: load first");
+    return svm_launch_apply(ctx);
+}
+
+__global__ void k_widen(const float *__restrict__ in, int64_t n, double *__restrict__ out) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (double)in[k];
+}
+
+static int svm_ensure_w64(fms_ctx *ctx) {
+    SvmState &S = ctx->svm;
+    if (S.w64_valid) return FMS_OK;
+    if (!S.loaded) return fail(ctx, FMS_ERR_STATE, "The SVM model has not been trained.");
+    FMS_CUDA(ctx, S.w64.alloc((size_t)S.dim));
+    k_widen<<<(S.dim + 255) / 256, 256, 0, ctx->stream>>>(S.w.p, S.dim, S.w64.p);
+    FMS_LAUNCH_CHECK(ctx);
+    S.w64_valid = true;
+    S.w64_dim = S.dim;
+    return FMS_OK;
+}
+
+FMS_API int fms_svm_get_weights(fms_ctx *ctx, double *w, int32_t dim) {
+    CHECK_CTX(ctx);
+    SvmState &S = ctx->svm;
+    FMS_TRY(svm_ensure_w64(ctx));
+    if (!w || dim != S.w64_dim) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_get_weights: dim %d != model dim %d", dim, S.w64_dim);
+    FMS_CUDA(ctx, cudaMemcpyAsync(w, S.w64.p, (size_t)dim * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
+FMS_API int fms_svm_set_weights(fms_ctx *ctx, const double *w, int32_t dim) {
+    CHECK_CTX(ctx);
+    if (!w || dim < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_set_weights: null or dim < 1");
+    SvmState &S = ctx->svm;
+    FMS_CUDA(ctx, S.w64.alloc((size_t)dim));
+    FMS_CUDA(ctx, cudaMemcpyAsync(S.w64.p, w, (size_t)dim * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    S.w64_valid = true;
+    S.w64_dim = dim;
+    return FMS_OK;
+}
+
+FMS_API int fms_svm_get_alpha(fms_ctx *ctx, double *alpha, int64_t n) {
+    CHECK_CTX(ctx);
+    SvmState &S = ctx->svm;
+    if (!S.loaded) return fail(ctx, FMS_ERR_STATE, "fms_svm_get_alpha: load first");
+    if (n != S.n || (n && !alpha)) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_get_alpha: n mismatch");
+    if (!n) return FMS_OK;
+    DevBuf<double> tmp;
+    FMS_CUDA(ctx, tmp.alloc((size_t)n));
+    k_widen<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(S.alpha.p, n, tmp.p);
+    FMS_LAUNCH_CHECK(ctx);
+    FMS_CUDA(ctx, cudaMemcpyAsync(alpha, tmp.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
+FMS_API int fms_svm_fit(fms_ctx *ctx, const void *X, int x_dtype, const int64_t *csr_ptr, const int32_t *csr_idx, const double *y,
+                        int64_t n, int32_t dim, const int32_t *block_id, int blocks, int iterations, int64_t local_iterations,
+                        double regularization, double stepsize, int64_t seed, int rng_mode, double *w_out) {
+    CHECK_CTX(ctx);
+    if (iterations < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_fit: iterations < 0");
+    if (!w_out) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_fit: w_out is null");
+    FMS_TRY(fms_svm_load(ctx, X, x_dtype, 0, csr_ptr, csr_idx, y, n, dim, block_id, blocks, 0, 1, regularization, stepsize, seed, rng_mode));
+    for (int t = 0; t < iterations; ++t) {
+        FMS_TRY(svm_launch_sweep(ctx, local_iterations));
+        FMS_TRY(svm_launch_apply(ctx));
+    }
+    return fms_svm_get_weights(ctx, w_out, dim);
+}
+
+FMS_API int fms_svm_predict(fms_ctx *ctx, const void *X, int x_dtype, const int64_t *csr_ptr, const int32_t *csr_idx, int64_t n,
+                            int32_t dim, const double *w, double threshold, int output_decision_function, double *out) {
+    CHECK_CTX(ctx);
+    SvmState &S = ctx->svm;
+    if (n < 0 || dim < 1 || (n && (!X || !out))) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_predict: bad arguments");
+    if (x_dtype < FMS_X_DENSE_F32 || x_dtype > FMS_X_CSR_F64) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_predict: x_dtype %d", x_dtype);
+    if (x_dtype == FMS_X_CSR_F64 && n && (!csr_ptr || !csr_idx)) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_predict: CSR arrays missing");
+    DevBuf<double> dw_in;
+    const double *d_w = nullptr;
+    if (w) {
+        FMS_CUDA(ctx, dw_in.alloc((size_t)dim));
+        FMS_CUDA(ctx, cudaMemcpyAsync(dw_in.p, w, (size_t)dim * 8, cudaMemcpyHostToDevice, ctx->stream));
+        d_w = dw_in.p;
+    } else {
+        if (!S.w64_valid && !S.loaded) return fail(ctx, FMS_ERR_STATE, "The SVM model has not been trained. Call first fit before calling the predict operation.");
+        FMS_TRY(svm_ensure_w64(ctx));
+        if (dim != S.w64_dim) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_predict: dim %d != model dim %d", dim, S.w64_dim);
+        d_w = S.w64.p;
+    }
+    if (!n) return FMS_OK;
+    DevBuf<unsigned char> dX;
+    DevBuf<int64_t> dptr;
+    DevBuf<int32_t> didx;
+    DevBuf<double> dout;
+    FMS_CUDA(ctx, dout.alloc((size_t)n));
+    size_t xbytes;
+    if (x_dtype == FMS_X_CSR_F64) {
+        const int64_t nnz = csr_ptr[n];
+        xbytes = (size_t)nnz * 8;
+        FMS_CUDA(ctx, dptr.alloc((size_t)n + 1));
+        FMS_CUDA(ctx, didx.alloc((size_t)nnz));
+        FMS_CUDA(ctx, cudaMemcpyAsync(dptr.p, csr_ptr, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (nnz) FMS_CUDA(ctx, cudaMemcpyAsync(didx.p, csr_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        xbytes = (size_t)n * dim * (x_dtype == FMS_X_DENSE_F32 ? 4 : 8);
+    }
+    FMS_CUDA(ctx, dX.alloc(xbytes));
+    if (xbytes) FMS_CUDA(ctx, cudaMemcpyAsync(dX.p, X, xbytes, cudaMemcpyHostToDevice, ctx->stream));
+    FMS_TRY(svm_predict_device(ctx, dX.p, x_dtype, dptr.p, didx.p, n, dim, d_w, threshold, output_decision_function, dout.p));
+    FMS_CUDA(ctx, cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
+// ====================================================================================================== debug
+__global__ void k_index_stream(long long seed, int block, int bound, long long count, int32_t *out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        JRand r;
+        r.s = JRand::scramble(seed ^ (long long)block);
+        for (long long i = 0; i < count; ++i) out[i] = r.next_int_bound(bound);
+    }
+}
+
+FMS_API int fms_debug_index_stream(fms_ctx *ctx, int64_t seed, int block, int32_t bound, int64_t count, int32_t *out) {
+    CHECK_CTX(ctx);
+    if (bound < 1 || count < 0 || (count && !out)) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_debug_index_stream: bad arguments");
+    if (!count) return FMS_OK;
+    DevBuf<int32_t> d;
+    FMS_CUDA(ctx, d.alloc((size_t)count));
+    k_index_stream<<<1, 32, 0, ctx->stream>>>((long long)seed, block, bound, (long long)count, d.p);
+    FMS_LAUNCH_CHECK(ctx);
+    FMS_CUDA(ctx, cudaMemcpyAsync(out, d.p, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,201 @@
+// common.cuh -- context, error plumbing and small device helpers shared by every translation unit of
+// libflinkms_b200.so.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/flinkms.h"
+
+namespace fms {
+
+// --------------------------------------------------------------------------------------------- buffers
+// Device allocation owned by the ctx; freed in the destructor (stream-ordered frees are not needed:
+// every (re)allocation happens between synchronised phases of fit/load).
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// --------------------------------------------------------------------------------------------- ALS state
+struct AlsState {
+    bool loaded = false, inited = false;
+    int64_t nnz = 0, n_users = 0, n_items = 0;
+    int shard_index = 0, shard_count = 1;
+    int64_t shard_rows[2] = {0, 0};          // S = ceil(N / shard_count) per side
+    int rank = 0;
+    int kernel = FMS_ALS_KERNEL_AUTO;
+    DevBuf<int64_t> ids[2];                  // sorted distinct ids (createBlockInformation)
+    DevBuf<int64_t> ptr[2];                  // CSR row pointers  (side 0: by user, side 1: by item)
+    DevBuf<int32_t> col[2];                  // dense partner index, ascending inside a row
+    DevBuf<float> val[2];                    // rating
+    DevBuf<float> fac[2];                    // factor matrices, fp32 row-major, rows_padded x rank
+    DevBuf<double> fac64[2];                 // fp64 copies for the predict path (lazy / external model)
+    bool fac64_valid = false;
+    bool model_external = false;             // installed via fms_als_set_model (no CSR)
+    DevBuf<int> info;                        // [0] = rows with non-positive pivot in the last half-step
+    int64_t last_bad = 0;
+    // tensor-core path: split-precision gather planes (hi | lo fp16) per side, refreshed after each update
+    DevBuf<uint16_t> plane[2];
+    bool plane_valid[2] = {false, false};
+    DevBuf<int32_t> order[2];                // row schedule (rows sorted by length, longest first)
+};
+
+// --------------------------------------------------------------------------------------------- SVM state
+struct SvmState {
+    bool loaded = false;
+    int64_t n = 0;
+    int32_t dim = 0;
+    int blocks = 0;
+    int shard_index = 0, shard_count = 1;
+    int x_kind = FMS_X_DENSE_F32;            // device layout: dense fp32 or CSR (fp32 values)
+    double lambda = 1.0, stepsize = 1.0;
+    int64_t seed = 0;
+    int rng_mode = FMS_RNG_PER_BLOCK;
+    int kernel = FMS_SVM_KERNEL_AUTO;
+    const float *X = nullptr;                // dense rows (owned buffer or caller's device pointer)
+    DevBuf<float> X_own;
+    DevBuf<int64_t> csr_ptr;
+    DevBuf<int32_t> csr_idx;
+    DevBuf<float> csr_val;
+    DevBuf<float> y;
+    DevBuf<float> alpha, alpha_tmp;          // persistent alpha, working copy (stepsize != 1)
+    DevBuf<int64_t> rows;                    // row ids grouped by block, arrival order inside a block
+    DevBuf<int64_t> blk_ptr;                 // blocks + 1 offsets into rows
+    std::vector<int64_t> h_blk_ptr;
+    DevBuf<uint64_t> rng;                    // per-block java.util.Random state (48-bit), persists across rounds
+    DevBuf<float> w;                         // dim
+    DevBuf<float> dw_blocks;                 // blocks_local x dim partial deltas
+    DevBuf<float> delta;                     // dim: sum over this rank's blocks
+    DevBuf<double> w64;                      // weights for the predict path
+    bool w64_valid = false;
+    int32_t w64_dim = 0;
+    std::vector<int> local_blocks;           // block ids swept by this rank
+    DevBuf<int32_t> d_local_blocks;
+};
+
+}  // namespace fms
+
+struct fms_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    fms::AlsState als;
+    fms::SvmState svm;
+};
+
+namespace fms {
+
+inline int fail(fms_ctx *ctx, int code, const char *fmt, ...) __attribute__((format(printf, 3, 4)));
+inline int fail(fms_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define FMS_CUDA(ctx, expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return ::fms::fail((ctx), e__ == cudaErrorMemoryAllocation ? FMS_ERR_OOM : FMS_ERR_CUDA,      \
+                               "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));   \
+    } while (0)
+
+#define FMS_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != FMS_OK) return rc__; \
+    } while (0)
+
+#define FMS_LAUNCH_CHECK(ctx)                                   \
+    do {                                                        \
+        ++(ctx)->launches;                                      \
+        FMS_CUDA((ctx), cudaGetLastError());                    \
+    } while (0)
+
+// --------------------------------------------------------------------------------------------- java.util.Random
+// 48-bit LCG of the JDK specification; bit-exact on the device.
+struct JRand {
+    unsigned long long s;
+    __host__ __device__ static unsigned long long scramble(long long seed) {
+        return ((unsigned long long)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);
+    }
+    __host__ __device__ int next(int bits) {
+        s = (s * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+        return (int)(long long)(s >> (48 - bits));
+    }
+    __host__ __device__ int next_int_bound(int bound) {
+        int r = next(31);
+        int m = bound - 1;
+        if ((bound & m) == 0) return (int)(((long long)bound * (long long)r) >> 31);
+        for (int u = r;; u = next(31)) {
+            r = u % bound;
+            if ((int)((unsigned)u - (unsigned)r + (unsigned)m) >= 0) return r;
+        }
+    }
+    __host__ __device__ double next_double() {
+        long long hi = (long long)next(26);
+        long long lo = (long long)next(27);
+        return (double)((hi << 27) + lo) * 0x1.0p-53;
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- internal entry points implemented across translation units ----
+int als_build_csr(fms_ctx *ctx, const int64_t *h_user, const int64_t *h_item, const double *h_rating, int64_t nnz);
+int als_launch_init(fms_ctx *ctx, int64_t seed);
+int als_launch_half_step_generic(fms_ctx *ctx, int which, float lambda, int64_t row_begin, int64_t row_end);
+int als_tc_supported(const fms_ctx *ctx, int rank);
+int als_launch_half_step_tc(fms_ctx *ctx, int which, float lambda, int64_t row_begin, int64_t row_end);
+int als_tc_refresh_planes(fms_ctx *ctx, int which);
+int als_predict_device(fms_ctx *ctx, const int64_t *d_u, const int64_t *d_i, int64_t n, double *d_out, uint8_t *d_found);
+int als_ensure_fac64(fms_ctx *ctx);
+int svm_launch_sweep(fms_ctx *ctx, int64_t local_iterations);
+int svm_launch_reduce_delta(fms_ctx *ctx);
+int svm_launch_apply(fms_ctx *ctx);
+int svm_predict_device(fms_ctx *ctx, const void *d_X, int x_kind, const int64_t *d_ptr, const int32_t *d_idx, int64_t n,
+                       int32_t dim, const double *d_w, double threshold, int decision, double *d_out);
+
+}  // namespace fms

@@ -1,0 +1,135 @@
+"""One-process-per-GPU sharding of the two hot paths over torch.distributed (NCCL on GPUs, gloo in CPU tests).
+
+ALS: every rank holds the full CSR pair and full factor replicas, solves the row shard
+[g*S, (g+1)*S) of the side being updated, then the shards are ALL-GATHERED into every replica -- the exchange
+Flink does with a join + coGroup network shuffle between half-steps (Appendix A.1 `updateFactors` message
+build).  Per-row arithmetic is identical to the 1-GPU run, so results are bitwise equal.
+
+SVM: rank g sweeps the CoCoA blocks k with k % G == g; the per-rank sum of block deltas (dim floats) is
+ALL-REDUCED and every rank applies w += (stepsize / blocks) * delta -- FlinkML's broadcast of w and
+union+reduce of the K delta vectors (Appendix A.2).
+
+The compute backend is any object with the small interface used below; the product backend is
+`_native.Context` (CUDA kernels through the C-ABI).  torch is plumbing only: device views + collectives.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def device_view(ptr: int, numel: int, dtype=torch.float32, device="cuda:0") -> torch.Tensor:
+    """Zero-copy torch view of `numel` elements at raw device address `ptr` (memory owned by the fms_ctx)."""
+    typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8"}[dtype]
+
+    class _Iface:
+        pass
+
+    w = _Iface()
+    w.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(w, device=device)
+
+
+def shard_range(n: int, world: int, rank: int):
+    """Rows [begin, end) of rank `rank`: S = ceil(n / world) rows per shard, last shards may be short or empty."""
+    s = (n + world - 1) // world
+    b = min(n, s * rank)
+    return b, min(n, b + s), s
+
+
+class ContextALSBackend:
+    """Adapts a `_native.Context` (ratings already loaded with this rank's shard) to DistributedALS."""
+
+    def __init__(self, ctx, device):
+        self.ctx = ctx
+        self.device = device
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    def half_step(self, which, lam):
+        self.ctx.als_half_step(which, lam)
+
+    def factor_tensor(self, which, rank):
+        ptr, rows_padded, b, e = self.ctx.als_factors_device(which)
+        return device_view(ptr, rows_padded * rank, torch.float32, self.device).view(rows_padded, rank)
+
+    def updated(self, which):
+        self.ctx.als_factors_updated(which)
+
+
+class DistributedALS:
+    """iterate(T){ users = f(items); items = f(users) }; users = f(items), sharded by rows."""
+
+    def __init__(self, backend, rank_dim: int, group=None):
+        self.b = backend
+        self.rank_dim = rank_dim
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def exchange(self, which):
+        if self.world == 1:
+            return
+        full = self.b.factor_tensor(which, self.rank_dim)               # (S * world, rank)
+        s = full.shape[0] // self.world
+        me = dist.get_rank(self.group)
+        stream = getattr(self.b, "stream", None)
+        if stream is not None:
+            with torch.cuda.stream(stream):                              # order the collective after the solve kernel
+                dist.all_gather_into_tensor(full, full[me * s:(me + 1) * s], group=self.group)
+        else:
+            dist.all_gather_into_tensor(full, full[me * s:(me + 1) * s].clone(), group=self.group)
+        self.b.updated(which)
+
+    def half_step(self, which, lam):
+        self.b.half_step(which, lam)
+        self.exchange(which)
+
+    def iteration(self, lam):
+        self.half_step(0, lam)
+        self.half_step(1, lam)
+
+    def fit(self, iterations, lam):
+        for _ in range(iterations):
+            self.iteration(lam)
+        self.half_step(0, lam)
+
+
+class ContextSVMBackend:
+    def __init__(self, ctx, device):
+        self.ctx = ctx
+        self.device = device
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    def sweep(self, local_iterations):
+        self.ctx.svm_sweep(local_iterations)
+
+    def delta_tensor(self):
+        ptr, dim = self.ctx.svm_delta_device()
+        return device_view(ptr, dim, torch.float32, self.device)
+
+    def apply(self):
+        self.ctx.svm_apply_delta()
+
+
+class DistributedSVM:
+    """CoCoA outer round: local block sweeps -> all-reduce(sum) of the delta -> w += scaling * delta."""
+
+    def __init__(self, backend, group=None):
+        self.b = backend
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def round(self, local_iterations):
+        self.b.sweep(local_iterations)
+        if self.world > 1:
+            delta = self.b.delta_tensor()
+            stream = getattr(self.b, "stream", None)
+            if stream is not None:
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.group)
+        self.b.apply()
+
+    def fit(self, iterations, local_iterations):
+        for _ in range(iterations):
+            self.round(local_iterations)

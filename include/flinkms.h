@@ -1,0 +1,162 @@
+/*
+ * flinkms.h -- C-ABI of libflinkms_b200.so: the B200-native replacement for the FlinkML 1.3.1 hot paths
+ * that mmziyad/flink-ms calls (ALS.fit/predict, SVM.fit/predict, queryable-state lookup-and-dot).
+ *
+ * The reference defines no FFI of its own; each entry point below names the reference call site whose
+ * work it takes over (paths relative to the reference root, per-file line numbers).  A JVM host binds
+ * these through the JNI shim shown in INTEGRATION.md; tests bind them through ctypes.
+ *
+ * Conventions
+ *   - return 0 (FMS_OK) or a negative fms_status; the message is fms_last_error(ctx) (ctx-owned, valid
+ *     until the next call on that ctx).  The JNI shim turns non-zero into a RuntimeException.
+ *   - caller owns every in/out HOST buffer; pointers are never retained past the call.
+ *   - the library owns all device memory inside fms_ctx.  A ctx is bound to ONE GPU (one process per GPU;
+ *     multi-GPU runs use one ctx per rank and exchange the device buffers exposed below with NCCL).
+ *   - a ctx is NOT thread-safe (the reference calls fit once from the driver thread, ALSImpl.scala:52,
+ *     and uses one lookup helper per operator thread, SGD.java:137, MSE.java:112).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns FMS_ERR_CUDA.
+ *   - ids are int64 (FlinkML widens Int to Long), values are IEEE double at the ABI like the reference
+ *     types ((Int,Int,Double) ALSImpl.scala:29; Array[Double] ALSImpl.scala:83; DenseVector.data
+ *     SVMImpl.scala:34).  Device arithmetic is fp32 (documented in DESIGN.md) unless noted.
+ */
+#ifndef FLINKMS_H
+#define FLINKMS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FMS_API __attribute__((visibility("default")))
+#else
+#define FMS_API
+#endif
+
+typedef struct fms_ctx fms_ctx;
+
+typedef enum fms_status {
+    FMS_OK = 0,
+    FMS_ERR_INVALID_ARG = -1,  /* null pointer, negative size, id out of range ...                     */
+    FMS_ERR_CUDA = -2,         /* CUDA runtime/driver error, or no device                               */
+    FMS_ERR_STATE = -3,        /* e.g. predict before fit ("The ALS model has not been fitted.")        */
+    FMS_ERR_UNSUPPORTED = -4,  /* configuration outside what the kernels cover (rank > 128, ...)        */
+    FMS_ERR_OOM = -5           /* device or host allocation failed                                      */
+} fms_status;
+
+/* x_dtype of the SVM design matrix */
+enum { FMS_X_DENSE_F32 = 0, FMS_X_DENSE_F64 = 1, FMS_X_CSR_F64 = 2 };
+/* SVM RNG schedule (SURVEY.md Appendix A.2 "determinism traps") */
+enum { FMS_RNG_PER_BLOCK = 0, FMS_RNG_SHARED_SUBTASK = 1 };
+/* which factor matrix */
+enum { FMS_USERS = 0, FMS_ITEMS = 1 };
+/* ALS solver selection: AUTO picks the tensor-core kernel when the rank supports it */
+enum { FMS_ALS_KERNEL_AUTO = 0, FMS_ALS_KERNEL_GENERIC = 1, FMS_ALS_KERNEL_TC = 2 };
+/* SVM sweep selection */
+enum { FMS_SVM_KERNEL_AUTO = 0, FMS_SVM_KERNEL_GENERIC = 1, FMS_SVM_KERNEL_WARP = 2 };
+
+/* ------------------------------------------------------------------------------------------------
+ * context
+ * ---------------------------------------------------------------------------------------------- */
+/* n_devices must be 1 (one process per GPU).  device_ids may be NULL => current device. */
+FMS_API int fms_create(fms_ctx **out, const int *device_ids, int n_devices);
+FMS_API void fms_destroy(fms_ctx *ctx);
+FMS_API const char *fms_last_error(const fms_ctx *ctx);
+FMS_API int fms_version(void);
+/* raw cudaStream_t all of this ctx's kernels are launched on (for CUDA-event timing by the host) */
+FMS_API void *fms_stream(fms_ctx *ctx);
+FMS_API int fms_synchronize(fms_ctx *ctx);
+/* number of kernel launches issued by this ctx since creation (bench.py's gpu_launches) */
+FMS_API int64_t fms_launch_count(const fms_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * ALS -- replaces `als.fit(inputDS, parameters)` (flink-als/.../ALSImpl.scala:35-52) and the
+ * `factorsOption` read-out (ALSImpl.scala:55-57).
+ * ---------------------------------------------------------------------------------------------- */
+/* Whole fit from host COO triples: createBlockInformation (sorted distinct ids, by-user and by-item CSR),
+ * items <- Random(id ^ seed).nextDouble x rank, `iterations` x {users, items} half-steps, final users
+ * half-step.  ALS-WR regularisation lambda * n_u.  Results stay in ctx. */
+FMS_API int fms_als_fit(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t nnz,
+                        int rank, int iterations, double lambda, int64_t seed,
+                        /*out*/ int64_t *n_users, int64_t *n_items);
+/* (ids ascending, row-major N x rank doubles).  Either out pointer may be NULL. */
+FMS_API int fms_als_get_factors(fms_ctx *ctx, int which, int64_t *ids, double *factors);
+/* Install an externally trained model (e.g. parsed `id,U|I,f1;f2;...` rows, ALSImpl.scala:84) for predict. */
+FMS_API int fms_als_set_model(fms_ctx *ctx, const int64_t *user_ids, const double *user_factors, int64_t n_users,
+                              const int64_t *item_ids, const double *item_factors, int64_t n_items, int rank);
+/* ALS.predict / the serve-side lookup-and-dot (flink-queryable-client/.../ALSPredictRandom.java:63-92,
+ * ALSPredict.java:65-83): out[k] = U[u_k] . I[i_k] (fp64 accumulate); found[k] = 0 when either id is not in
+ * the model (the reference reports "Factors do not exist" and skips; out[k] is then 0). */
+FMS_API int fms_als_predict(fms_ctx *ctx, const int64_t *u, const int64_t *i, int64_t n, double *out, uint8_t *found);
+/* MSE.java:122-160 (als-ms evaluation): mean squared error of the model on held-out ratings, missing ids
+ * skipped; *n_used receives the number of ratings scored. */
+FMS_API int fms_als_mse(fms_ctx *ctx, const int64_t *u, const int64_t *i, const double *rating, int64_t n,
+                        double *mse, int64_t *n_used);
+
+/* --- step-level ALS API: data resident in HBM, used by bench.py (`value`) and by the one-process-per-GPU
+ *     sharded driver (flink-ms_b200/dist.py), which all-gathers the factor shards between half-steps. --- */
+/* Upload + index the ratings.  Every rank holds the full CSR pair and full factor replicas and SOLVES only
+ * rows [shard_index*S, (shard_index+1)*S) with S = ceil(N / shard_count). */
+FMS_API int fms_als_load(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t nnz,
+                         int shard_index, int shard_count, /*out*/ int64_t *n_users, int64_t *n_items);
+FMS_API int fms_als_init(fms_ctx *ctx, int rank, int64_t seed);
+/* One updateFactors pass over this rank's shard: which = FMS_USERS solves users from items. */
+FMS_API int fms_als_half_step(fms_ctx *ctx, int which, double lambda);
+/* Device view of a factor matrix for collectives: fp32 row-major, rows_padded = S * shard_count rows of
+ * `rank` floats; shard rows are [shard_begin, shard_end). */
+FMS_API int fms_als_factors_device(fms_ctx *ctx, int which, void **dev_ptr, int64_t *rows_padded,
+                                   int64_t *shard_begin, int64_t *shard_end);
+/* Tell the library a factor matrix was rewritten from outside (after an all-gather) so derived device
+ * state (split-precision gather planes of the tensor-core kernel) is refreshed. */
+FMS_API int fms_als_factors_updated(fms_ctx *ctx, int which);
+/* number of rows whose Cholesky hit a non-positive pivot in the last half-step (dposv info != 0; FlinkML
+ * ignores it, so do we -- exposed for tests). */
+FMS_API int fms_als_last_info(fms_ctx *ctx, int64_t *bad_rows);
+FMS_API int fms_als_set_kernel(fms_ctx *ctx, int kernel);
+
+/* ------------------------------------------------------------------------------------------------
+ * SVM -- replaces `svm.fit(trainingDS)` (flink-svm/.../SVMImpl.scala:24-29) and `weightsOption`
+ * (SVMImpl.scala:31-35).  CoCoA outer loop, SDCA local solver, hinge loss.
+ * ---------------------------------------------------------------------------------------------- */
+/* block_id[i] in [0, blocks): CoCoA block of row i (FlinkMLTools.block assigns by source subtask, an
+ * input-split property, hence explicit).  local_iterations <= 0 => H = n_k (one epoch per round).
+ * scaling = stepsize / blocks (configured count).  w_out: dim doubles. */
+FMS_API int fms_svm_fit(fms_ctx *ctx, const void *X, int x_dtype, const int64_t *csr_ptr, const int32_t *csr_idx,
+                        const double *y, int64_t n, int32_t dim, const int32_t *block_id, int blocks, int iterations,
+                        int64_t local_iterations, double regularization, double stepsize, int64_t seed, int rng_mode,
+                        /*out*/ double *w_out);
+/* SVM.predict / serve-side SVMPredictRandom.java:68-88: raw = x.w (fp64); decision function or
+ * (raw > threshold ? 1.0 : -1.0), STRICT '>'.  w == NULL uses the last fitted / installed weights. */
+FMS_API int fms_svm_predict(fms_ctx *ctx, const void *X, int x_dtype, const int64_t *csr_ptr, const int32_t *csr_idx,
+                            int64_t n, int32_t dim, const double *w, double threshold, int output_decision_function,
+                            double *out);
+FMS_API int fms_svm_set_weights(fms_ctx *ctx, const double *w, int32_t dim);
+FMS_API int fms_svm_get_weights(fms_ctx *ctx, double *w, int32_t dim);
+FMS_API int fms_svm_get_alpha(fms_ctx *ctx, double *alpha, int64_t n);
+
+/* --- step-level SVM API (HBM-resident; sharded: this rank sweeps blocks k with k % shard_count ==
+ *     shard_index, the host all-reduces the delta buffer, every rank applies it). --- */
+/* X_is_device != 0: X (dense fp32 only) already lives on this ctx's GPU and is used in place. */
+FMS_API int fms_svm_load(fms_ctx *ctx, const void *X, int x_dtype, int X_is_device, const int64_t *csr_ptr,
+                         const int32_t *csr_idx, const double *y, int64_t n, int32_t dim, const int32_t *block_id,
+                         int blocks, int shard_index, int shard_count, double regularization, double stepsize,
+                         int64_t seed, int rng_mode);
+/* localDualMethod over this rank's blocks: fills the delta buffer with sum_k dw_k (fp32, dim floats). */
+FMS_API int fms_svm_sweep(fms_ctx *ctx, int64_t local_iterations);
+FMS_API int fms_svm_delta_device(fms_ctx *ctx, void **dev_ptr, int32_t *dim);
+/* w += (stepsize / blocks) * delta */
+FMS_API int fms_svm_apply_delta(fms_ctx *ctx);
+FMS_API int fms_svm_set_kernel(fms_ctx *ctx, int kernel);
+
+/* ------------------------------------------------------------------------------------------------
+ * java.util.Random on the device (bit-exact index selection): fills out[count] with the stream
+ * `new Random(seed ^ block).nextInt(bound)` exactly as the SDCA kernel draws it.  Test hook.
+ * ---------------------------------------------------------------------------------------------- */
+FMS_API int fms_debug_index_stream(fms_ctx *ctx, int64_t seed, int block, int32_t bound, int64_t count, int32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLINKMS_H */

@@ -1,0 +1,242 @@
+"""GPU parity tests for the ALS path: the CUDA kernels (through the C-ABI) against the fp64 oracle on the same
+seeded inputs.  Tolerances: one half-step from identical inputs <= 1e-5 relative (max-norm); a whole fit
+<= 1e-4 relative (BASELINE.json north_star); ids / found flags / init bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+HALF_TOL = 1e-5
+FIT_TOL = 1e-4
+
+
+def _case(fms, U, I, nnz, seed=1234, stride=(1, 1), offset=(0, 0)):
+    return fms.synth.als_ratings(U, I, nnz, seed, stride, offset)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _synth(fms):
+    import importlib
+    fms.synth = importlib.import_module("flink-ms_b200.synth")
+
+
+def _kernels(fms, rank):
+    ks = [fms._native.ALS_KERNEL_GENERIC]
+    if rank in (64, 128):
+        ks.append(fms._native.ALS_KERNEL_AUTO)
+    return ks
+
+
+@pytest.mark.parametrize("rank", [1, 8, 10, 16, 32, 64, 100, 128])
+def test_half_step_parity_from_identical_inputs(fms, ctx, rank):
+    u, i, r = _case(fms, 300, 200, 6000, seed=rank)
+    orc = oracle.OracleALS(u, i, r)
+    for kernel in _kernels(fms, rank):
+        ctx.als_set_kernel(kernel)
+        nu, ni = ctx.als_load(u, i, r)
+        assert (nu, ni) == (orc.n_users, orc.n_items)
+        ctx.als_init(rank, 42)
+        ids, Y0 = ctx.als_get_factors(fms._native.ITEMS)
+        orc.init(rank, 42)
+        oid, OY = orc.factors(1)
+        assert (ids == oid).all()
+        assert np.array_equal(Y0, OY.astype(np.float32).astype(np.float64))      # init: bit-exact RNG, fp32 storage
+        orc.set_factors(1, Y0)                                                    # identical inputs
+        ctx.als_half_step(fms._native.USERS, 0.9)
+        orc.half_step(0, 0.9)
+        _, X = ctx.als_get_factors(fms._native.USERS)
+        _, OX = orc.factors(0)
+        assert rel_err(X, OX) <= HALF_TOL, (kernel, rel_err(X, OX))
+        assert ctx.als_last_info() == 0
+        orc.set_factors(0, X)
+        ctx.als_half_step(fms._native.ITEMS, 0.9)
+        orc.half_step(1, 0.9)
+        _, Y = ctx.als_get_factors(fms._native.ITEMS)
+        _, OY1 = orc.factors(1)
+        assert rel_err(Y, OY1) <= HALF_TOL, (kernel, rel_err(Y, OY1))
+    ctx.als_set_kernel(fms._native.ALS_KERNEL_AUTO)
+
+
+def test_fit_parity_config1_rank8(fms, ctx):
+    """BASELINE.json configs[0]: rank 8, 10k x 10k, 100k ratings, T=10, lambda 0.9, seed 42."""
+    u, i, r = _case(fms, 10_000, 10_000, 100_000)
+    nu, ni = ctx.als_fit(u, i, r, 8, 10, 0.9, 42)
+    orc = oracle.OracleALS(u, i, r)
+    assert orc.fit(8, 10, 0.9, 42) == 0
+    for which in (0, 1):
+        ids, F = ctx.als_get_factors(which)
+        oid, OF = orc.factors(which)
+        assert (ids == oid).all()
+        assert rel_err(F, OF) <= FIT_TOL, rel_err(F, OF)
+
+
+@pytest.mark.parametrize("rank,kernel", [(64, "auto"), (64, "generic"), (128, "auto")])
+def test_fit_parity_rank64_128_long_rows(fms, ctx, rank, kernel):
+    # items get ~400 ratings each, users ~40: both row-length regimes of the bench configuration, scaled down
+    u, i, r = _case(fms, 4000, 400, 160_000, seed=5)
+    ctx.als_set_kernel(fms._native.ALS_KERNEL_GENERIC if kernel == "generic" else fms._native.ALS_KERNEL_AUTO)
+    ctx.als_fit(u, i, r, rank, 3, 0.9, 42)
+    ctx.als_set_kernel(fms._native.ALS_KERNEL_AUTO)
+    orc = oracle.OracleALS(u, i, r)
+    orc.fit(rank, 3, 0.9, 42)
+    for which in (0, 1):
+        _, F = ctx.als_get_factors(which)
+        _, OF = orc.factors(which)
+        assert rel_err(F, OF) <= FIT_TOL, (which, rel_err(F, OF))
+
+
+def test_golden_small_case_with_duplicates_and_sparse_ids(fms, ctx):
+    g = json.load(open(os.path.join(GOLD, "oracle_small.json")))["als"]
+    ctx.als_fit(g["user"], g["item"], g["rating"], g["rank"], g["iterations"], g["lambda"], g["seed"])
+    uid, X = ctx.als_get_factors(0)
+    iid, Y = ctx.als_get_factors(1)
+    assert uid.tolist() == g["user_ids"] and iid.tolist() == g["item_ids"]
+    assert rel_err(X, np.array(g["U"])) <= FIT_TOL and rel_err(Y, np.array(g["I"])) <= FIT_TOL
+
+
+def test_negative_and_huge_ids_and_zero_iterations(fms, ctx):
+    u, i, r = _case(fms, 50, 40, 600, seed=3, stride=(10 ** 12, 7), offset=(-5 * 10 ** 13, -100))
+    ctx.als_fit(u, i, r, 5, 0, 0.9, 42)              # T=0: items = init, users = one solve
+    orc = oracle.OracleALS(u, i, r)
+    orc.fit(5, 0, 0.9, 42)
+    iid, Y = ctx.als_get_factors(1)
+    oid, OY = orc.factors(1)
+    assert (iid == oid).all() and np.array_equal(Y, OY.astype(np.float32).astype(np.float64))
+    _, X = ctx.als_get_factors(0)
+    assert rel_err(X, orc.factors(0)[1]) <= HALF_TOL
+
+
+def test_single_rating_rows_and_single_row(fms, ctx):
+    u = np.array([5, 6, 7, 8], np.int64)
+    i = np.array([1, 1, 2, 3], np.int64)
+    r = np.array([4.0, 3.0, 5.0, 1.5])
+    ctx.als_fit(u, i, r, 3, 2, 0.9, 42)
+    orc = oracle.OracleALS(u, i, r)
+    orc.fit(3, 2, 0.9, 42)
+    for which in (0, 1):
+        assert rel_err(ctx.als_get_factors(which)[1], orc.factors(which)[1]) <= FIT_TOL
+
+
+def test_empty_input(fms, ctx):
+    e = np.zeros(0, np.int64)
+    assert ctx.als_fit(e, e, np.zeros(0), 4, 2, 0.9, 42) == (0, 0)
+    ids, F = ctx.als_get_factors(0)
+    assert ids.size == 0 and F.shape == (0, 4)
+    out, found = ctx.als_predict([1], [2])
+    assert found.tolist() == [False] and out.tolist() == [0.0]
+
+
+def test_argument_errors(fms, ctx):
+    u, i, r = _case(fms, 20, 20, 100)
+    with pytest.raises(fms.FlinkMSError) as e:
+        ctx.als_fit(u, i, r, 0, 1, 0.9, 42)
+    assert e.value.status == fms._native.ERR_INVALID_ARG
+    with pytest.raises(fms.FlinkMSError) as e:
+        ctx.als_fit(u, i, r, 129, 1, 0.9, 42)
+    assert e.value.status == fms._native.ERR_UNSUPPORTED
+    with pytest.raises(fms.FlinkMSError) as e:
+        ctx.als_fit(u, i, r, 4, -1, 0.9, 42)
+    assert e.value.status == fms._native.ERR_INVALID_ARG
+    fresh = fms.Context(0)
+    with pytest.raises(fms.FlinkMSError) as e:
+        fresh.als_predict([1], [1])
+    assert e.value.status == fms._native.ERR_STATE and "has not been fitted" in str(e.value)
+    fresh.close()
+
+
+def test_predict_and_mse_match_oracle(fms, ctx):
+    u, i, r = _case(fms, 500, 300, 8000, seed=11, stride=(3, 2), offset=(1, 5))
+    ctx.als_fit(u, i, r, 16, 2, 0.9, 42)
+    uid, X = ctx.als_get_factors(0)
+    iid, Y = ctx.als_get_factors(1)
+    orc = oracle.OracleALS(u, i, r)
+    orc.set_factors(0, X)
+    orc.set_factors(1, Y)
+    rng = np.random.default_rng(0)
+    qu = np.concatenate([rng.choice(u, 3000), [2, 10 ** 15, u[0]]])          # 2 and 1e15 are not user ids
+    qi = np.concatenate([rng.choice(i, 3000), [i[0], i[0], 4]])              # 4 is not an item id
+    out, found = ctx.als_predict(qu, qi)
+    oout, ofound = orc.predict(qu, qi)
+    assert np.array_equal(found, ofound)                                      # indexing: bit-exact
+    assert found[-3:].tolist() == [False, False, False]
+    assert np.allclose(out, oout, rtol=1e-13, atol=1e-15)                     # fp64 dot, order differs only
+    mse, used = ctx.als_mse(qu, qi, np.full(len(qu), 3.0))
+    assert used == int(found.sum())
+    assert mse == pytest.approx(np.mean((3.0 - oout[ofound]) ** 2), rel=1e-12)
+
+
+def test_external_model_lookup(fms, ctx):
+    """Serve-side path (ALSPredictRandom.java:63-92): install `id,U|I,f1;..` rows, batched lookup-and-dot."""
+    rng = np.random.default_rng(5)
+    uid = np.sort(rng.choice(10 ** 6, 1000, replace=False)).astype(np.int64)
+    iid = np.sort(rng.choice(10 ** 6, 800, replace=False)).astype(np.int64)
+    U = rng.standard_normal((1000, 10))
+    I = rng.standard_normal((800, 10))
+    c = fms.Context(0)
+    c.als_set_model(uid, U, iid, I)
+    qu = rng.choice(uid, 5000)
+    qi = rng.choice(iid, 5000)
+    out, found = c.als_predict(qu, qi)
+    want = np.einsum("kd,kd->k", U[np.searchsorted(uid, qu)], I[np.searchsorted(iid, qi)])
+    assert found.all() and np.allclose(out, want, rtol=1e-13, atol=1e-14)
+    with pytest.raises(fms.FlinkMSError):
+        c.als_set_model(uid[::-1].copy(), U, iid, I)                          # ids must ascend
+    c.close()
+
+
+def test_operator_api_matches_reference_call_shape(fms, ctx):
+    """ALSImpl.scala:35-57 written against the mirror."""
+    u, i, r = _case(fms, 200, 100, 3000, seed=2)
+    als = fms.ALS(ctx).setIterations(3).setNumFactors(6).setBlocks(4)
+    parameters = fms.ParameterMap().add(fms.ALS.Lambda, 0.9).add(fms.ALS.Seed, 42)
+    als.fit((u, i, r), parameters)
+    users, items = als.factorsOption
+    orc = oracle.OracleALS(u, i, r)
+    orc.fit(6, 3, 0.9, 42)
+    assert [f.id for f in users] == orc.factors(0)[0].tolist()
+    assert rel_err(items.factors, orc.factors(1)[1]) <= FIT_TOL
+    pu, pi, pred = als.predict(([u[0], 10 ** 9], [i[0], i[0]]))
+    assert pu.tolist() == [u[0]] and len(pred) == 1                            # unknown id dropped (inner join)
+
+
+def test_sharded_half_steps_equal_unsharded(fms, ctx):
+    """Two ctxs on one GPU play ranks 0/1: each solves its row shard, shards are exchanged by hand."""
+    import importlib
+
+    import torch
+    dv = importlib.import_module("flink-ms_b200.dist").device_view
+    u, i, r = _case(fms, 301, 203, 5000, seed=8)
+    ctx.als_load(u, i, r)
+    ctx.als_init(8, 42)
+    ctx.als_half_step(0, 0.9)
+    ctx.als_half_step(1, 0.9)
+    _, Yref = ctx.als_get_factors(1)
+    _, Xref = ctx.als_get_factors(0)
+    ranks = [fms.Context(0), fms.Context(0)]
+    for g, c in enumerate(ranks):
+        c.als_load(u, i, r, g, 2)
+        c.als_init(8, 42)
+    for which in (0, 1):
+        views = []
+        for c in ranks:
+            c.als_half_step(which, 0.9)
+            c.synchronize()
+            ptr, rows, b, e = c.als_factors_device(which)
+            views.append((dv(ptr, rows * 8).view(rows, 8), b, e))
+        for src in range(2):                       # the all-gather, by hand
+            t_src, b, e = views[src]
+            views[1 - src][0][b:e].copy_(t_src[b:e])
+        torch.cuda.synchronize()
+        for c in ranks:
+            c.als_factors_updated(which)
+    for c in ranks:
+        _, X = c.als_get_factors(0)
+        _, Y = c.als_get_factors(1)
+        assert np.array_equal(X, Xref) and np.array_equal(Y, Yref)             # same per-row math: bitwise equal
+        c.close()

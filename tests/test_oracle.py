@@ -1,0 +1,194 @@
+"""CPU tests of the oracle: java.util.Random KATs, C oracle vs the independent numpy restatement, linear-algebra
+and optimisation identities that do not depend on recollecting FlinkML."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import np_restatement as R
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_jrand_published_kats():
+    kat = json.load(open(os.path.join(GOLD, "jrand_kat.json")))["published"]
+    for seed, vals in kat["ints"].items():
+        assert oracle.jrand_ints(int(seed), len(vals)).tolist() == vals
+    for seed, vals in kat["doubles"].items():
+        assert oracle.jrand_doubles(int(seed), len(vals)).tolist() == vals     # bit-exact doubles
+    for key, vals in kat["bounded"].items():
+        seed, bound = map(int, key.split(":"))
+        assert oracle.jrand_bounded(seed, bound, len(vals)).tolist() == vals
+
+
+def test_jrand_derived_streams_match_python_ints():
+    kat = json.load(open(os.path.join(GOLD, "jrand_kat.json")))["derived"]
+    for key, vals in kat["bounded"].items():
+        seed, bound = map(int, key.split(":"))
+        assert oracle.jrand_bounded(seed, bound, len(vals)).tolist() == vals
+    for seed, vals in kat["doubles"].items():
+        assert oracle.jrand_doubles(int(seed), len(vals)).tolist() == vals
+    for seed, vals in kat["ints"].items():
+        assert oracle.jrand_ints(int(seed), len(vals)).tolist() == vals
+
+
+def test_jrand_rejection_path_is_exercised():
+    # bound just above 2^30 rejects ~half of the draws: the C loop and the Python loop must agree
+    bound = (1 << 30) + 1
+    r = R.JavaRandom(99)
+    want = [r.next_int(bound) for _ in range(200)]
+    assert oracle.jrand_bounded(99, bound, 200).tolist() == want
+    assert max(want) < bound and min(want) >= 0
+
+
+def _als_case(seed=1, U=60, I=50, nnz=900):
+    rng = np.random.default_rng(seed)
+    u = rng.integers(0, U, nnz) * 3 + 7
+    i = rng.integers(0, I, nnz) * 5 - 20
+    r = np.clip(np.round(rng.normal(3.5, 1, nnz) * 2) / 2, 0.5, 5)
+    return u, i, r
+
+
+def test_als_c_oracle_matches_numpy_restatement():
+    u, i, r = _als_case()
+    h = oracle.OracleALS(u, i, r)
+    assert h.fit(8, 5, 0.9, 42) == 0
+    uid, X = h.factors(0)
+    iid, Y = h.factors(1)
+    uid2, X2, iid2, Y2 = R.als_fit(u, i, r, 8, 5, 0.9, 42)
+    assert (uid == uid2).all() and (iid == iid2).all()
+    assert np.abs(X - X2).max() <= 1e-12 * np.abs(X2).max()
+    assert np.abs(Y - Y2).max() <= 1e-12 * np.abs(Y2).max()
+
+
+def test_als_rows_satisfy_normal_equations():
+    u, i, r = _als_case(3)
+    lam, d = 0.9, 7
+    h = oracle.OracleALS(u, i, r)
+    h.fit(d, 3, lam, 42)
+    uid, X = h.factors(0)
+    iid, Y = h.factors(1)
+    # returned users are the exact ALS-WR solve against the returned items
+    for row, user in enumerate(uid):
+        sel = u == user
+        V = Y[np.searchsorted(iid, i[sel])]
+        A = V.T @ V + lam * sel.sum() * np.eye(d)
+        assert np.allclose(A @ X[row], V.T @ r[sel], rtol=1e-10, atol=1e-10)
+
+
+def test_als_init_is_random_of_id_xor_seed():
+    u, i, r = _als_case(5)
+    h = oracle.OracleALS(u, i, r)
+    h.init(4, 42)
+    iid, Y = h.factors(1)
+    for k in (0, len(iid) // 2, len(iid) - 1):
+        rr = R.JavaRandom(int(iid[k]) ^ 42)
+        assert Y[k].tolist() == [rr.next_double() for _ in range(4)]
+
+
+def test_als_risk_non_increasing():
+    u, i, r = _als_case(9, nnz=1500)
+    lam = 0.9
+    h = oracle.OracleALS(u, i, r)
+    h.init(6, 42)
+    h.half_step(0, lam)
+    prev = h.risk(lam)
+    for _ in range(4):
+        for which in (1, 0):
+            h.half_step(which, lam)
+            cur = h.risk(lam)
+            assert cur <= prev * (1 + 1e-12)
+            prev = cur
+
+
+def test_als_duplicates_are_separate_ratings_and_golden():
+    g = json.load(open(os.path.join(GOLD, "oracle_small.json")))["als"]
+    h = oracle.OracleALS(g["user"], g["item"], g["rating"])
+    h.fit(g["rank"], g["iterations"], g["lambda"], g["seed"])
+    uid, X = h.factors(0)
+    iid, Y = h.factors(1)
+    assert uid.tolist() == g["user_ids"] and iid.tolist() == g["item_ids"]
+    assert np.allclose(X, np.array(g["U"]), rtol=1e-12, atol=1e-14)
+    assert np.allclose(Y, np.array(g["I"]), rtol=1e-12, atol=1e-14)
+    # the case holds duplicated (u,i) pairs: n_u counts every rating
+    pairs = list(zip(g["user"], g["item"]))
+    assert len(set(pairs)) < len(pairs)
+
+
+def test_als_predict_unknown_ids():
+    u, i, r = _als_case(2)
+    h = oracle.OracleALS(u, i, r)
+    h.fit(4, 1, 0.9, 42)
+    out, found = h.predict([u[0], 10 ** 9, u[1]], [i[0], i[0], -12345])
+    assert found.tolist() == [True, False, False]
+    uid, X = h.factors(0)
+    iid, Y = h.factors(1)
+    assert out[0] == pytest.approx(X[np.searchsorted(uid, u[0])] @ Y[np.searchsorted(iid, i[0])], rel=1e-14)
+
+
+def _svm_case(seed=1, n=400, D=24):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, D)).astype(np.float32)
+    ws = rng.standard_normal(D)
+    y = np.sign(X @ ws + 0.1 * rng.standard_normal(n))
+    y[y == 0] = 1
+    return X, y
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("H", [10, -1])
+def test_svm_c_oracle_matches_python_restatement(mode, H):
+    X, y = _svm_case()
+    K = 4
+    bid = np.arange(len(y)) % K
+    w, a = oracle.svm_fit(X, y, bid, K, 6, H, 1.0, 1.0, 42, mode, return_alpha=True)
+    w2, a2 = R.svm_fit(X, y, bid, K, 6, H, 1.0, 1.0, 42, mode)
+    assert np.abs(w - w2).max() <= 1e-13 * max(np.abs(w2).max(), 1e-300)
+    assert np.abs(a - a2).max() <= 1e-13
+
+
+def test_svm_alpha_box_and_dual_ascent_with_one_block():
+    X, y = _svm_case(4)
+    bid = np.zeros(len(y), np.int32)
+    prev = -1.0
+    for T in (1, 2, 4, 8):
+        # K=1, stepsize=1: CoCoA == plain SDCA, whose dual objective never decreases and w == w(alpha)
+        w, a = oracle.svm_fit(X, y, bid, 1, T, -1, 1.0, 1.0, 42, 0, return_alpha=True)
+        assert a.min() >= 0.0 and a.max() <= 1.0
+        p, d = oracle.svm_objectives(X, y, w, a, 1.0)
+        assert d >= prev - 1e-12 and p >= d - 1e-12
+        prev = d
+        w_of_alpha = (X.astype(np.float64) * (a * y)[:, None]).sum(0) / (1.0 * len(y))
+        assert np.allclose(w, w_of_alpha, rtol=1e-10, atol=1e-12)
+
+
+def test_svm_dtypes_agree_and_csr():
+    X, y = _svm_case(6, n=150, D=10)
+    X[::7] = 0.0                                    # all-zero rows: q == 0 -> alpha' = 1
+    K = 3
+    bid = np.arange(len(y)) % K
+    w32 = oracle.svm_fit(X, y, bid, K, 4, -1, 0.5, 0.7, 11, 0)
+    w64 = oracle.svm_fit(X.astype(np.float64), y, bid, K, 4, -1, 0.5, 0.7, 11, 0)
+    ptr = np.arange(0, X.size + 1, X.shape[1])
+    idx = np.tile(np.arange(X.shape[1]), X.shape[0])
+    wcsr = oracle.svm_fit(None, y, bid, K, 4, -1, 0.5, 0.7, 11, 0, csr=(ptr, idx, X.astype(np.float64).ravel()), dim=X.shape[1])
+    assert np.array_equal(w32, w64) and np.allclose(w32, wcsr, rtol=1e-13, atol=1e-15)
+
+
+def test_svm_golden_and_index_stream():
+    g = json.load(open(os.path.join(GOLD, "oracle_small.json")))["svm"]
+    X = np.array(g["X"], np.float32)
+    w10 = oracle.svm_fit(X, g["y"], g["block_id"], g["blocks"], g["iterations"], 10, 1.0, 1.0, g["seed"], 0)
+    wep = oracle.svm_fit(X, g["y"], g["block_id"], g["blocks"], g["iterations"], -1, 1.0, 1.0, g["seed"], 0)
+    assert np.allclose(w10, g["w_H10"], rtol=1e-12, atol=1e-15) and np.allclose(wep, g["w_epoch"], rtol=1e-12, atol=1e-15)
+    r = R.JavaRandom(42 ^ 3)
+    assert oracle.svm_index_stream(42, 3, 50, 40).tolist() == [r.next_int(50) for _ in range(40)]
+
+
+def test_svm_predict_strict_threshold():
+    X = np.array([[1.0, 0.0], [0.0, 0.0], [-1.0, 0.0]])
+    w = np.array([2.0, 5.0])
+    assert oracle.svm_predict(X, w, 0.0, False).tolist() == [1.0, -1.0, -1.0]      # raw == threshold -> -1
+    assert oracle.svm_predict(X, w, 0.0, True).tolist() == [2.0, 0.0, -2.0]
