@@ -367,6 +367,9 @@ FMS_API int fms_svm_load(fms_ctx *ctx, const void *X, int x_dtype, int X_is_devi
     FMS_CUDA(ctx, S.rows.alloc((size_t)n));
     FMS_CUDA(ctx, S.blk_ptr.alloc((size_t)blocks + 1));
     if (n) FMS_CUDA(ctx, cudaMemcpyAsync(S.rows.p, rows.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    std::vector<int32_t> rows32(rows.begin(), rows.end());
+    FMS_CUDA(ctx, S.rows32.alloc((size_t)n));
+    if (n) FMS_CUDA(ctx, cudaMemcpyAsync(S.rows32.p, rows32.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     FMS_CUDA(ctx, cudaMemcpyAsync(S.blk_ptr.p, cnt.data(), ((size_t)blocks + 1) * 8, cudaMemcpyHostToDevice, st));
     S.local_blocks.clear();
     for (int k = 0; k < blocks; ++k) if (k % shard_count == shard_index) S.local_blocks.push_back(k);

@@ -86,6 +86,7 @@ struct SvmState {
     DevBuf<float> y;
     DevBuf<float> alpha, alpha_tmp;          // persistent alpha, working copy (stepsize != 1)
     DevBuf<int64_t> rows;                    // row ids grouped by block, arrival order inside a block
+    DevBuf<int32_t> rows32;                  // same, 32-bit (n < 2^31): what the warp sweep reads
     DevBuf<int64_t> blk_ptr;                 // blocks + 1 offsets into rows
     std::vector<int64_t> h_blk_ptr;
     DevBuf<uint64_t> rng;                    // per-block java.util.Random state (48-bit), persists across rounds

@@ -177,7 +177,7 @@ int svm_launch_sweep(fms_ctx *ctx, int64_t local_iterations) {
     bool use_warp = false;
     if (S.kernel != FMS_SVM_KERNEL_GENERIC && S.rng_mode == FMS_RNG_PER_BLOCK) use_warp = svm_warp_supported(ctx) != 0;
     if (S.kernel == FMS_SVM_KERNEL_WARP && !use_warp)
-        return fail(ctx, FMS_ERR_UNSUPPORTED, "warp SVM sweep needs dense fp32 X, dim %% 128 == 0, dim <= 2048, per-block RNG");
+        return fail(ctx, FMS_ERR_UNSUPPORTED, "warp SVM sweep needs dense fp32 X, dim %% 128 == 0, dim <= 1024, per-block RNG");
     if (use_warp) {
         FMS_TRY(svm_launch_sweep_warp(ctx, alpha_work, local_iterations));
     } else {
