@@ -61,6 +61,7 @@ SIGNATURES = {
     "fms_svm_apply_delta": (C.c_int, [_vp]),
     "fms_svm_set_kernel": (C.c_int, [_vp, C.c_int]),
     "fms_debug_index_stream": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int32, C.c_int64, _i32p]),
+    "fms_debug_als_gramian": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_float)]),
 }
 
 _lib = None
@@ -301,6 +302,13 @@ class Context:
         self._check(self._lib.fms_svm_predict(self._h, xp, dt, pp, ip, n, dim, _p(wv, _f64p), threshold,
                                               int(bool(output_decision_function)), _p(out, _f64p)))
         return out
+
+    def debug_als_gramian(self, which, lam, row_begin, row_end):
+        rank = self._als_shape[2]
+        out = np.empty((row_end - row_begin, rank * rank + rank), np.float32)
+        self._check(self._lib.fms_debug_als_gramian(self._h, which, lam, row_begin, row_end,
+                                                    out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out[:, :rank * rank].reshape(-1, rank, rank), out[:, rank * rank:]
 
     def debug_index_stream(self, seed, block, bound, count):
         out = np.empty(count, np.int32)

@@ -582,4 +582,23 @@ FMS_API int fms_debug_index_stream(fms_ctx *ctx, int64_t seed, int block, int32_
     return FMS_OK;
 }
 
+FMS_API int fms_debug_als_gramian(fms_ctx *ctx, int which, double lambda, int64_t row_begin, int64_t row_end, float *out) {
+    CHECK_CTX(ctx);
+    AlsState &A = ctx->als;
+    if (!A.loaded || !A.inited) return fail(ctx, FMS_ERR_STATE, "fms_debug_als_gramian: load + init first");
+    if (which != 0 && which != 1) return fail(ctx, FMS_ERR_INVALID_ARG, "which = %d", which);
+    const int64_t n = which == 0 ? A.n_users : A.n_items;
+    if (row_begin < 0 || row_end > n || row_end < row_begin || !out) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_debug_als_gramian: bad row range");
+    if (!als_tc_supported(ctx, A.rank)) return fail(ctx, FMS_ERR_UNSUPPORTED, "tensor-core ALS kernel does not cover rank %d", A.rank);
+    const size_t per = (size_t)A.rank * A.rank + A.rank;
+    DevBuf<float> d;
+    FMS_CUDA(ctx, d.alloc((size_t)(row_end - row_begin) * per));
+    FMS_CUDA(ctx, cudaMemsetAsync(A.info.p, 0, sizeof(int), ctx->stream));
+    FMS_TRY(als_tc_dump(ctx, which, (float)lambda, row_begin, row_end, d.p));
+    FMS_CUDA(ctx, cudaMemcpyAsync(out, d.p, (size_t)(row_end - row_begin) * per * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    A.fac64_valid = false;
+    return FMS_OK;
+}
+
 }  // extern "C"

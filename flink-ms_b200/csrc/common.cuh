@@ -191,6 +191,7 @@ int als_launch_half_step_generic(fms_ctx *ctx, int which, float lambda, int64_t 
 int als_tc_supported(const fms_ctx *ctx, int rank);
 int als_launch_half_step_tc(fms_ctx *ctx, int which, float lambda, int64_t row_begin, int64_t row_end);
 int als_tc_refresh_planes(fms_ctx *ctx, int which);
+int als_tc_dump(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t re, float *d_dump);
 int als_predict_device(fms_ctx *ctx, const int64_t *d_u, const int64_t *d_i, int64_t n, double *d_out, uint8_t *d_found);
 int als_ensure_fac64(fms_ctx *ctx);
 int svm_launch_sweep(fms_ctx *ctx, int64_t local_iterations);

@@ -155,6 +155,10 @@ FMS_API int fms_svm_set_kernel(fms_ctx *ctx, int kernel);
  * `new Random(seed ^ block).nextInt(bound)` exactly as the SDCA kernel draws it.  Test hook.
  * ---------------------------------------------------------------------------------------------- */
 FMS_API int fms_debug_index_stream(fms_ctx *ctx, int64_t seed, int block, int32_t bound, int64_t count, int32_t *out);
+/* Test hook for the tensor-core ALS kernel (rank 64): runs it over rows [row_begin, row_end) of side `which` and
+ * returns, per row, the 64x64 system matrix (Gramian + lambda*n on the diagonal, row-major) followed by the 64
+ * right-hand-side values, exactly as the solver warps receive them.  Side effect: those rows are also solved. */
+FMS_API int fms_debug_als_gramian(fms_ctx *ctx, int which, double lambda, int64_t row_begin, int64_t row_end, float *out);
 
 #ifdef __cplusplus
 }
