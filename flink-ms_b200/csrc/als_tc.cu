@@ -29,11 +29,11 @@ constexpr int TILE_BYTES = KROWS * 128;           // one plane (hi or lo) of one
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;
 constexpr int NSTG = 16;                          // ring depth (64 KB)
 constexpr int NACC = 4;                           // TMEM accumulator slots (128 columns each: D1 | D2)
-constexpr int NGB = 4;                            // Gramian hand-off buffers == solver warps
+constexpr int NGB = 8;                            // Gramian hand-off buffers: two per solver warp
 constexpr int GLD = 68;                           // padded row pitch of a hand-off buffer (floats)
-constexpr int N_EPI = 4, N_SOLVE = 4, N_LOAD = 3; // warps per role (+1 MMA warp)
+constexpr int N_EPI = 4, N_SOLVE = 4, N_LOAD = 7; // warps per role (+1 MMA warp)
 constexpr int W_EPI0 = 0, W_SOLVE0 = 4, W_MMA = 8, W_LOAD0 = 9;
-constexpr int NWARPS = 12;
+constexpr int NWARPS = 16;
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
 struct Smem {
@@ -43,8 +43,9 @@ struct Smem {
     static constexpr int gbuf = bpart + NSTG * D * 4;                       // NGB x 64 x GLD floats
     static constexpr int bacc = gbuf + NGB * D * GLD * 4;                   // NACC x 64 floats (+ n)
     static constexpr int bsol = bacc + NACC * (D + 4) * 4;                  // NGB x (64 floats + n + row)
-    static constexpr int colb = bsol + NGB * (D + 4) * 4;                   // NGB x 68 floats (pivot column)
-    static constexpr int bars = colb + NGB * 72 * 4;                        // mbarriers
+    static constexpr int colb = bsol + NGB * (D + 4) * 4;                   // N_SOLVE x 64 floats (1 / L_jj)
+    static constexpr int lring = colb + N_SOLVE * D * 4;                    // N_LOAD x 4 x 32 words (index ring)
+    static constexpr int bars = lring + N_LOAD * 4 * 32 * 4;                // mbarriers
     static constexpr int n_bars = 2 * NSTG + 2 * NACC + 2 * NGB;
     static constexpr int tmem_ptr = bars + n_bars * 8;
     static constexpr int total = tmem_ptr + 16;
@@ -70,6 +71,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!ok);
+}
+// long waits (epilogue / solver hand-offs): back off so the spinning warp does not eat issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(100);
+    }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -161,55 +179,113 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
 
     if (warp >= W_LOAD0) {
         // ================================================================== loaders
+        // Loader warp lw owns the CTA's stages lw, lw + N_LOAD, ...  Three-deep software pipeline per warp:
+        //   index  (IA stages ahead): lanes 0-15 read col/val of the stage's 16 ratings, park them in a small
+        //                              shared ring and prefetch the partner rows into L2
+        //   gather (1 stage ahead)   : 8 x LDG.128 per lane into one of two register buffers
+        //   convert (current)        : fp32 -> fp16 hi / lo planes in UMMA layout, b partial, signal the MMA warp
         const int lw = warp - W_LOAD0;
         const int half = lane >> 4, sub = lane & 15;
         const float4 *P4 = reinterpret_cast<const float4 *>(P);
-        uint32_t stage_ctr = 0;                                   // global stage counter of this CTA
-        for (int64_t row = first; row < row_end; row += stride) {
-            const int64_t s0 = ptr[row], e0 = ptr[row + 1];
-            const int nst = (int)((e0 - s0 + KROWS - 1) / KROWS);
-            for (int st = 0; st < nst; ++st, ++stage_ctr) {
-                if ((int)(stage_ctr % N_LOAD) != lw) continue;
-                const int slot = stage_ctr % NSTG;
-                const int64_t k0 = s0 + (int64_t)st * KROWS;
-                float4 v[8];
-                float rt[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int64_t k = k0 + 2 * i + half;
-                    const bool ok = k < e0;
-                    const int32_t c = ok ? col[k] : 0;
-                    rt[i] = ok ? val[k] : 0.f;
-                    v[i] = ok ? P4[(int64_t)c * (D / 4) + sub] : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                mbar_wait(bar_empty(slot), ((stage_ctr / NSTG) & 1) ^ 1);
-                unsigned char *hi_t = sm + Smem::ring + slot * STAGE_BYTES;
-                unsigned char *lo_t = hi_t + TILE_BYTES;
-                float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = 2 * i + half;
-                    bp.x = fmaf(rt[i], v[i].x, bp.x); bp.y = fmaf(rt[i], v[i].y, bp.y);
-                    bp.z = fmaf(rt[i], v[i].z, bp.z); bp.w = fmaf(rt[i], v[i].w, bp.w);
-                    const __half2 h01 = __floats2half2_rn(v[i].x, v[i].y), h23 = __floats2half2_rn(v[i].z, v[i].w);
-                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                    const __half2 l01 = __floats2half2_rn((v[i].x - f01.x) * LO_SCALE, (v[i].y - f01.y) * LO_SCALE);
-                    const __half2 l23 = __floats2half2_rn((v[i].z - f23.x) * LO_SCALE, (v[i].w - f23.y) * LO_SCALE);
-                    // 128-byte swizzle: 16-byte chunk index ^= row & 7 (tiles are 1024-byte aligned)
-                    const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)sub >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)sub & 1u) * 8u;
-                    uint2 hv, lv;
-                    hv.x = *reinterpret_cast<const uint32_t *>(&h01); hv.y = *reinterpret_cast<const uint32_t *>(&h23);
-                    lv.x = *reinterpret_cast<const uint32_t *>(&l01); lv.y = *reinterpret_cast<const uint32_t *>(&l23);
-                    *reinterpret_cast<uint2 *>(hi_t + off) = hv;
-                    *reinterpret_cast<uint2 *>(lo_t + off) = lv;
-                }
-                bp.x += __shfl_xor_sync(0xffffffffu, bp.x, 16); bp.y += __shfl_xor_sync(0xffffffffu, bp.y, 16);
-                bp.z += __shfl_xor_sync(0xffffffffu, bp.z, 16); bp.w += __shfl_xor_sync(0xffffffffu, bp.w, 16);
-                if (half == 0) reinterpret_cast<float4 *>(sm + Smem::bpart + slot * D * 4)[sub] = bp;
-                fence_proxy_async();                              // generic-proxy stores -> visible to the tensor core
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_full(slot));
+        constexpr int IA = 3, IRING = 4;
+        int *iring = reinterpret_cast<int *>(sm + Smem::lring + lw * IRING * 32 * 4);   // [IRING][16 idx | 16 rating bits]
+
+        struct It { int64_t row, s0, e0; uint32_t base, nst; };
+        auto it_init = [&](It &it) {
+            it.row = first; it.base = 0; it.nst = 0; it.s0 = it.e0 = 0;
+            if (it.row < row_end) { it.s0 = ptr[it.row]; it.e0 = ptr[it.row + 1]; it.nst = (uint32_t)((it.e0 - it.s0 + KROWS - 1) / KROWS); }
+        };
+        // position the iterator on global stage counter c; false when the CTA has no such stage
+        auto it_seek = [&](It &it, uint32_t c) -> bool {
+            while (it.row < row_end && c >= it.base + it.nst) {
+                it.base += it.nst;
+                it.row += stride;
+                if (it.row < row_end) { it.s0 = ptr[it.row]; it.e0 = ptr[it.row + 1]; it.nst = (uint32_t)((it.e0 - it.s0 + KROWS - 1) / KROWS); }
             }
+            return it.row < row_end;
+        };
+        It it_i, it_g;
+        it_init(it_i); it_init(it_g);
+
+        auto do_index = [&](uint32_t n) {
+            const uint32_t c = (uint32_t)lw + n * N_LOAD;
+            if (!it_seek(it_i, c)) return;
+            const int64_t k = it_i.s0 + (int64_t)(c - it_i.base) * KROWS + sub;
+            if (half == 0) {
+                const bool ok = k < it_i.e0;
+                const int32_t ci = ok ? col[k] : -1;
+                const float rv = ok ? val[k] : 0.f;
+                int *slot = iring + (n % IRING) * 32;
+                const int pos = (sub & 1) * 8 + (sub >> 1);       // rows of one half-warp become contiguous
+                slot[pos] = ci;
+                slot[16 + pos] = __float_as_int(rv);
+                if (ok) {
+                    const char *rp = reinterpret_cast<const char *>(P + (int64_t)ci * D);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 128));
+                }
+            }
+        };
+        auto do_gather = [&](uint32_t n, float4 (&v)[8], float (&rt)[8]) -> bool {
+            const uint32_t c = (uint32_t)lw + n * N_LOAD;
+            if (!it_seek(it_g, c)) return false;
+            __syncwarp();                                          // ring entries written by lanes 0-15 of this warp
+            const int *slot = iring + (n % IRING) * 32;
+            const int4 i0 = *reinterpret_cast<const int4 *>(slot + half * 8), i1 = *reinterpret_cast<const int4 *>(slot + half * 8 + 4);
+            const int4 r0 = *reinterpret_cast<const int4 *>(slot + 16 + half * 8), r1 = *reinterpret_cast<const int4 *>(slot + 16 + half * 8 + 4);
+            const int ci[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+            const int ri[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                rt[i] = __int_as_float(ri[i]);
+                v[i] = ci[i] >= 0 ? P4[(int64_t)ci[i] * (D / 4) + sub] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            return true;
+        };
+        auto do_convert = [&](uint32_t n, const float4 (&v)[8], const float (&rt)[8]) {
+            const uint32_t c = (uint32_t)lw + n * N_LOAD;
+            const int slot = c % NSTG;
+            mbar_wait(bar_empty(slot), ((c / NSTG) & 1) ^ 1);
+            unsigned char *hi_t = sm + Smem::ring + slot * STAGE_BYTES;
+            unsigned char *lo_t = hi_t + TILE_BYTES;
+            float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 2 * i + half;
+                bp.x = fmaf(rt[i], v[i].x, bp.x); bp.y = fmaf(rt[i], v[i].y, bp.y);
+                bp.z = fmaf(rt[i], v[i].z, bp.z); bp.w = fmaf(rt[i], v[i].w, bp.w);
+                const __half2 h01 = __floats2half2_rn(v[i].x, v[i].y), h23 = __floats2half2_rn(v[i].z, v[i].w);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn((v[i].x - f01.x) * LO_SCALE, (v[i].y - f01.y) * LO_SCALE);
+                const __half2 l23 = __floats2half2_rn((v[i].z - f23.x) * LO_SCALE, (v[i].w - f23.y) * LO_SCALE);
+                // 128-byte swizzle: 16-byte chunk index ^= row & 7 (tiles are 1024-byte aligned)
+                const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)sub >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)sub & 1u) * 8u;
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const uint32_t *>(&h01); hv.y = *reinterpret_cast<const uint32_t *>(&h23);
+                lv.x = *reinterpret_cast<const uint32_t *>(&l01); lv.y = *reinterpret_cast<const uint32_t *>(&l23);
+                *reinterpret_cast<uint2 *>(hi_t + off) = hv;
+                *reinterpret_cast<uint2 *>(lo_t + off) = lv;
+            }
+            bp.x += __shfl_xor_sync(0xffffffffu, bp.x, 16); bp.y += __shfl_xor_sync(0xffffffffu, bp.y, 16);
+            bp.z += __shfl_xor_sync(0xffffffffu, bp.z, 16); bp.w += __shfl_xor_sync(0xffffffffu, bp.w, 16);
+            if (half == 0) reinterpret_cast<float4 *>(sm + Smem::bpart + slot * D * 4)[sub] = bp;
+            fence_proxy_async();                                  // generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full(slot));
+        };
+
+        float4 va[8], vb[8];
+        float ra[8], rb[8];
+        for (uint32_t n = 0; n < IA; ++n) do_index(n);
+        bool have_a = do_gather(0, va, ra), have_b = false;
+        for (uint32_t n = 0; have_a; n += 2) {
+            do_index(n + IA);
+            have_b = do_gather(n + 1, vb, rb);
+            do_convert(n, va, ra);
+            if (!have_b) break;
+            do_index(n + 1 + IA);
+            have_a = do_gather(n + 2, va, ra);
+            do_convert(n + 1, vb, rb);
         }
     } else if (warp == W_MMA) {
         // ================================================================== MMA issuer (+ b reduction on lanes 0-15)
@@ -296,80 +372,199 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
         }
     } else {
         // ================================================================== solvers: one warp per system
-        const int g = warp - W_SOLVE0;
-        float *cb = reinterpret_cast<float *>(sm + Smem::colb + g * 72 * 4);
-        uint32_t use = 0;
+        // Lane l owns matrix rows l and l+32 in registers.  Right-looking Cholesky in 16 rank-4 panel steps written as
+        // two LOOPS (panels over columns 0..31, then 32..63) so the code stays instruction-cache resident: the
+        // register window is rotated by 4 columns per panel (folded into the last FFMA2 of the panel, no moves).
+        // The finished L columns go back into the hand-off buffer (column-major, pitch GLD) where the trailing
+        // updates (broadcast LDS.128 + packed FFMA2) and the back substitution read them.  Forward substitution is
+        // fused (b is carried as an extra column).
+        const int sv = warp - W_SOLVE0;
+        float *invd = reinterpret_cast<float *>(sm + Smem::colb + sv * D * 4);
         uint32_t job = 0;
         for (int64_t row = first; row < row_end; row += stride, ++job) {
-            if ((int)(job % NGB) != g) continue;
-            mbar_wait(bar_g_full(g), use & 1);
-            const float *G = reinterpret_cast<const float *>(sm + Smem::gbuf + g * D * GLD * 4);
+            if ((int)(job % N_SOLVE) != sv) continue;
+            const int g = job % NGB;
+            mbar_wait_sleep(bar_g_full(g), (job / NGB) & 1);
+            float *G = reinterpret_cast<float *>(sm + Smem::gbuf + g * D * GLD * 4);
             const float *bi = reinterpret_cast<const float *>(sm + Smem::bsol + g * (D + 4) * 4);
-            float a0[D + 1], a1[D + 1];                           // rows `lane` and `lane + 32`, augmented with b
+            float2 A0[16], A1a[16], A1b[16];                      // row l cols 0..31 | row l+32 cols 0..31 | row l+32 cols 32..63
 #pragma unroll
-            for (int c = 0; c < D; c += 4) {
-                const float4 x0 = *reinterpret_cast<const float4 *>(G + lane * GLD + c);
-                const float4 x1 = *reinterpret_cast<const float4 *>(G + (lane + 32) * GLD + c);
-                a0[c] = x0.x; a0[c + 1] = x0.y; a0[c + 2] = x0.z; a0[c + 3] = x0.w;
-                a1[c] = x1.x; a1[c + 1] = x1.y; a1[c + 2] = x1.z; a1[c + 3] = x1.w;
+            for (int c = 0; c < 8; ++c) {
+                const float4 x0 = *reinterpret_cast<const float4 *>(G + lane * GLD + 4 * c);
+                const float4 x1 = *reinterpret_cast<const float4 *>(G + (lane + 32) * GLD + 4 * c);
+                const float4 x2 = *reinterpret_cast<const float4 *>(G + (lane + 32) * GLD + 32 + 4 * c);
+                A0[2 * c] = make_float2(x0.x, x0.y); A0[2 * c + 1] = make_float2(x0.z, x0.w);
+                A1a[2 * c] = make_float2(x1.x, x1.y); A1a[2 * c + 1] = make_float2(x1.z, x1.w);
+                A1b[2 * c] = make_float2(x2.x, x2.y); A1b[2 * c + 1] = make_float2(x2.z, x2.w);
             }
-            a0[D] = bi[lane];
-            a1[D] = bi[lane + 32];
+            float b0 = bi[lane], b1 = bi[lane + 32];
             if (DUMP) {
                 float *o = dump + (int64_t)(row - row_begin) * (D * D + D);
+                for (int c = 0; c < D; ++c) { o[lane * D + c] = G[lane * GLD + c]; o[(lane + 32) * D + c] = G[(lane + 32) * GLD + c]; }
+                o[D * D + lane] = b0; o[D * D + lane + 32] = b1;
+            }
+            __syncwarp();                                         // every lane holds its rows: the buffer becomes L storage
+            float *Ls = G;                                        // Ls[j * GLD + i] = L[i][j]
+            bool bad = false;
+
+            // ---------------- panels over columns 0..31 (pivot rows live in A0 / b0 of lanes j0..j0+3)
+#pragma unroll 1
+            for (int j0 = 0; j0 < 32; j0 += 4) {
+                const float d00 = __shfl_sync(0xffffffffu, A0[0].x, j0);
+                const float d10 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 1), d11 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 1);
+                const float d20 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 2), d21 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 2);
+                const float d22 = __shfl_sync(0xffffffffu, A0[1].x, j0 + 2);
+                const float d30 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 3), d31 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 3);
+                const float d32 = __shfl_sync(0xffffffffu, A0[1].x, j0 + 3), d33 = __shfl_sync(0xffffffffu, A0[1].y, j0 + 3);
+                const float zb0 = __shfl_sync(0xffffffffu, b0, j0), zb1 = __shfl_sync(0xffffffffu, b0, j0 + 1);
+                const float zb2 = __shfl_sync(0xffffffffu, b0, j0 + 2), zb3 = __shfl_sync(0xffffffffu, b0, j0 + 3);
+                // 4x4 Cholesky of the diagonal block, redundantly in every lane
+                bad |= !(d00 > 0.f);
+                const float i0 = rsqrt_refined(d00);
+                const float l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
+                const float t11 = fmaf(-l10, l10, d11);
+                bad |= !(t11 > 0.f);
+                const float i1 = rsqrt_refined(t11);
+                const float l21 = fmaf(-l20, l10, d21) * i1, l31 = fmaf(-l30, l10, d31) * i1;
+                const float t22 = fmaf(-l21, l21, fmaf(-l20, l20, d22));
+                bad |= !(t22 > 0.f);
+                const float i2 = rsqrt_refined(t22);
+                const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, d32)) * i2;
+                const float t33 = fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, d33)));
+                bad |= !(t33 > 0.f);
+                const float i3 = rsqrt_refined(t33);
+                // forward substitution for the panel's right-hand side
+                const float z0 = zb0 * i0;
+                const float z1 = fmaf(-z0, l10, zb1) * i1;
+                const float z2 = fmaf(-z1, l21, fmaf(-z0, l20, zb2)) * i2;
+                const float z3 = fmaf(-z2, l32, fmaf(-z1, l31, fmaf(-z0, l30, zb3))) * i3;
+                // my two rows of the panel: x = A[i][J] * Ld^-T
+                const float p0 = A0[0].x * i0;
+                const float p1 = fmaf(-p0, l10, A0[0].y) * i1;
+                const float p2 = fmaf(-p1, l21, fmaf(-p0, l20, A0[1].x)) * i2;
+                const float p3 = fmaf(-p2, l32, fmaf(-p1, l31, fmaf(-p0, l30, A0[1].y))) * i3;
+                const float q0 = A1a[0].x * i0;
+                const float q1 = fmaf(-q0, l10, A1a[0].y) * i1;
+                const float q2 = fmaf(-q1, l21, fmaf(-q0, l20, A1a[1].x)) * i2;
+                const float q3 = fmaf(-q2, l32, fmaf(-q1, l31, fmaf(-q0, l30, A1a[1].y))) * i3;
+                // right-hand side: rows below the panel get b_i -= sum_c L[i][c] z_c; pivot rows keep z
+                const float nb0 = fmaf(-p3, z3, fmaf(-p2, z2, fmaf(-p1, z1, fmaf(-p0, z0, b0))));
+                b1 = fmaf(-q3, z3, fmaf(-q2, z2, fmaf(-q1, z1, fmaf(-q0, z0, b1))));
+                const int rel = lane - j0;
+                b0 = rel == 0 ? z0 : rel == 1 ? z1 : rel == 2 ? z2 : rel == 3 ? z3 : rel > 3 ? nb0 : b0;   // finished rows keep z
+                // publish the four L columns (column-major) and 1 / L_jj
+                float *Lc = Ls + j0 * GLD;
+                Lc[lane] = p0; Lc[GLD + lane] = p1; Lc[2 * GLD + lane] = p2; Lc[3 * GLD + lane] = p3;
+                Lc[lane + 32] = q0; Lc[GLD + lane + 32] = q1; Lc[2 * GLD + lane + 32] = q2; Lc[3 * GLD + lane + 32] = q3;
+                if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(i0, i1, i2, i3);
+                __syncwarp();
+                // trailing update; the window (positions 2..15 = columns j0+4..j0+31) shifts down by two float2
+                const float pm[4] = {-p0, -p1, -p2, -p3}, qm[4] = {-q0, -q1, -q2, -q3};
+                float2 N0[16], N1[16];
 #pragma unroll
-                for (int c = 0; c < D; ++c) { o[lane * D + c] = a0[c]; o[(lane + 32) * D + c] = a1[c]; }
-                o[D * D + lane] = a0[D]; o[D * D + lane + 32] = a1[D];
+                for (int w = 0; w < 14; ++w) { N0[w] = A0[w + 2]; N1[w] = A1a[w + 2]; }
+                N0[14] = N0[15] = N1[14] = N1[15] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float2 pp = make_float2(pm[c], pm[c]), qq = make_float2(qm[c], qm[c]);
+                    const float *col_c = Lc + c * GLD + j0 + 4;                       // L[j0+4 ..][j0+c]
+#pragma unroll
+                    for (int w4 = 0; w4 < 7; ++w4) {
+                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
+                        const float2 la = make_float2(lv.x, lv.y), lb = make_float2(lv.z, lv.w);
+                        N0[2 * w4] = __ffma2_rn(pp, la, N0[2 * w4]); N0[2 * w4 + 1] = __ffma2_rn(pp, lb, N0[2 * w4 + 1]);
+                        N1[2 * w4] = __ffma2_rn(qq, la, N1[2 * w4]); N1[2 * w4 + 1] = __ffma2_rn(qq, lb, N1[2 * w4 + 1]);
+                    }
+                    const float *col_s = Lc + c * GLD + 32;                           // L[32 ..][j0+c]
+#pragma unroll
+                    for (int w4 = 0; w4 < 8; ++w4) {
+                        const float4 lv = *reinterpret_cast<const float4 *>(col_s + 4 * w4);
+                        A1b[2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A1b[2 * w4]);
+                        A1b[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A1b[2 * w4 + 1]);
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < 16; ++w) { A0[w] = N0[w]; A1a[w] = N1[w]; }
+            }
+            // ---------------- panels over columns 32..63 (pivot rows live in A1b / b1 of lanes j0-32 .. +3)
+#pragma unroll 1
+            for (int j0 = 32; j0 < 64; j0 += 4) {
+                const int src = j0 - 32;
+                const float d00 = __shfl_sync(0xffffffffu, A1b[0].x, src);
+                const float d10 = __shfl_sync(0xffffffffu, A1b[0].x, src + 1), d11 = __shfl_sync(0xffffffffu, A1b[0].y, src + 1);
+                const float d20 = __shfl_sync(0xffffffffu, A1b[0].x, src + 2), d21 = __shfl_sync(0xffffffffu, A1b[0].y, src + 2);
+                const float d22 = __shfl_sync(0xffffffffu, A1b[1].x, src + 2);
+                const float d30 = __shfl_sync(0xffffffffu, A1b[0].x, src + 3), d31 = __shfl_sync(0xffffffffu, A1b[0].y, src + 3);
+                const float d32 = __shfl_sync(0xffffffffu, A1b[1].x, src + 3), d33 = __shfl_sync(0xffffffffu, A1b[1].y, src + 3);
+                const float zb0 = __shfl_sync(0xffffffffu, b1, src), zb1 = __shfl_sync(0xffffffffu, b1, src + 1);
+                const float zb2 = __shfl_sync(0xffffffffu, b1, src + 2), zb3 = __shfl_sync(0xffffffffu, b1, src + 3);
+                bad |= !(d00 > 0.f);
+                const float i0 = rsqrt_refined(d00);
+                const float l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
+                const float t11 = fmaf(-l10, l10, d11);
+                bad |= !(t11 > 0.f);
+                const float i1 = rsqrt_refined(t11);
+                const float l21 = fmaf(-l20, l10, d21) * i1, l31 = fmaf(-l30, l10, d31) * i1;
+                const float t22 = fmaf(-l21, l21, fmaf(-l20, l20, d22));
+                bad |= !(t22 > 0.f);
+                const float i2 = rsqrt_refined(t22);
+                const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, d32)) * i2;
+                const float t33 = fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, d33)));
+                bad |= !(t33 > 0.f);
+                const float i3 = rsqrt_refined(t33);
+                const float z0 = zb0 * i0;
+                const float z1 = fmaf(-z0, l10, zb1) * i1;
+                const float z2 = fmaf(-z1, l21, fmaf(-z0, l20, zb2)) * i2;
+                const float z3 = fmaf(-z2, l32, fmaf(-z1, l31, fmaf(-z0, l30, zb3))) * i3;
+                const float q0 = A1b[0].x * i0;
+                const float q1 = fmaf(-q0, l10, A1b[0].y) * i1;
+                const float q2 = fmaf(-q1, l21, fmaf(-q0, l20, A1b[1].x)) * i2;
+                const float q3 = fmaf(-q2, l32, fmaf(-q1, l31, fmaf(-q0, l30, A1b[1].y))) * i3;
+                const float nb1 = fmaf(-q3, z3, fmaf(-q2, z2, fmaf(-q1, z1, fmaf(-q0, z0, b1))));
+                const int rel = lane - src;
+                b1 = rel == 0 ? z0 : rel == 1 ? z1 : rel == 2 ? z2 : rel == 3 ? z3 : rel > 3 ? nb1 : b1;
+                float *Lc = Ls + j0 * GLD;
+                Lc[lane + 32] = q0; Lc[GLD + lane + 32] = q1; Lc[2 * GLD + lane + 32] = q2; Lc[3 * GLD + lane + 32] = q3;
+                if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(i0, i1, i2, i3);
+                __syncwarp();
+                const float qm[4] = {-q0, -q1, -q2, -q3};
+                float2 N1[16];
+#pragma unroll
+                for (int w = 0; w < 14; ++w) N1[w] = A1b[w + 2];
+                N1[14] = N1[15] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float2 qq = make_float2(qm[c], qm[c]);
+                    const float *col_c = Lc + c * GLD + j0 + 4;
+#pragma unroll
+                    for (int w4 = 0; w4 < 7; ++w4) {
+                        // columns beyond 63 fall into the next L column / padding: finite garbage that is never used
+                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
+                        N1[2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), N1[2 * w4]);
+                        N1[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), N1[2 * w4 + 1]);
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < 16; ++w) A1b[w] = N1[w];
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_g_empty(g));           // every lane has its rows in registers
-            ++use;
-            bool bad = false;
-            // ---- right-looking Cholesky, forward substitution fused as column D
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                const float pj = (j < 32) ? a0[j] : a1[j];
-                const float ajj = __shfl_sync(0xffffffffu, pj, j & 31);
-                bad |= !(ajj > 0.f);
-                const float inv = rsqrt_refined(ajj);
-                a0[j] *= inv;                                     // L[l][j]   (row j itself: sqrt(ajj))
-                a1[j] *= inv;                                     // L[l+32][j]
-                const float bj = (j < 32) ? a0[D] : a1[D];
-                const float zj = __shfl_sync(0xffffffffu, bj, j & 31) * inv;
-                if ((j & 31) == lane) { if (j < 32) a0[D] = zj; else a1[D] = zj; }
-                if (j + 1 < D) {
-                    cb[lane] = a0[j];
-                    cb[lane + 32] = a1[j];
-                    __syncwarp();
-                    // trailing update of my two rows: a[i][k] -= L[i][j] * L[k][j], k = j+1 .. 63
-                    const float l0 = a0[j], l1 = a1[j];
-#pragma unroll
-                    for (int k4 = (j + 1) & ~3; k4 < D; k4 += 4) {
-                        const float4 c4 = *reinterpret_cast<const float4 *>(cb + k4);
-                        if (k4 + 0 > j) { a0[k4 + 0] = fmaf(-l0, c4.x, a0[k4 + 0]); a1[k4 + 0] = fmaf(-l1, c4.x, a1[k4 + 0]); }
-                        if (k4 + 1 > j) { a0[k4 + 1] = fmaf(-l0, c4.y, a0[k4 + 1]); a1[k4 + 1] = fmaf(-l1, c4.y, a1[k4 + 1]); }
-                        if (k4 + 2 > j) { a0[k4 + 2] = fmaf(-l0, c4.z, a0[k4 + 2]); a1[k4 + 2] = fmaf(-l1, c4.z, a1[k4 + 2]); }
-                        if (k4 + 3 > j) { a0[k4 + 3] = fmaf(-l0, c4.w, a0[k4 + 3]); a1[k4 + 3] = fmaf(-l1, c4.w, a1[k4 + 3]); }
-                    }
-                    __syncwarp();
-                }
-                // b_i -= L[i][j] * z_j for the rows below j
-                if (lane > j) a0[D] = fmaf(-a0[j], zj, a0[D]);
-                if (lane + 32 > j) a1[D] = fmaf(-a1[j], zj, a1[D]);
-            }
-            // ---- back substitution L^T x = z
+            // ---------------- back substitution L^T x = z (column sweep): b0 / b1 hold z and turn into x
             float x0 = 0.f, x1 = 0.f;
-#pragma unroll
-            for (int j = D - 1; j >= 0; --j) {
-                float part = 0.f;
-                if (lane > j) part = a0[j] * x0;
-                if (lane + 32 > j) part = fmaf(a1[j], x1, part);
-                part = warp_sum(part);
-                if ((j & 31) == lane) {
-                    if (j < 32) x0 = (a0[D] - part) / a0[j];
-                    else x1 = (a1[D] - part) / a1[j];
-                }
+#pragma unroll 1
+            for (int j = D - 1; j >= 32; --j) {
+                const float xj = __shfl_sync(0xffffffffu, b1, j - 32) * invd[j];
+                if (lane == j - 32) x1 = xj;
+                b0 = fmaf(-Ls[lane * GLD + j], xj, b0);                               // L[j][lane], lane < 32 <= j
+                if (lane + 32 < j) b1 = fmaf(-Ls[(lane + 32) * GLD + j], xj, b1);
             }
+#pragma unroll 1
+            for (int j = 31; j >= 0; --j) {
+                const float xj = __shfl_sync(0xffffffffu, b0, j) * invd[j];
+                if (lane == j) x0 = xj;
+                if (lane < j) b0 = fmaf(-Ls[lane * GLD + j], xj, b0);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_g_empty(g));           // L storage no longer needed
             T[row * D + lane] = x0;
             T[row * D + lane + 32] = x1;
             if (bad && lane == 0) atomicAdd(info, 1);
