@@ -1,21 +1,29 @@
-// als_tc.cu -- K1 on the 5th-generation tensor cores (rank 64): warp-specialised persistent kernel
+// als_tc.cu -- K1 on the 5th-generation tensor cores (rank 64): warp-specialised persistent kernel, one CTA per SM.
 //
-//   loader warps   : gather partner rows (fp32, LDG.128), split each value into fp16 hi + fp16 lo*2^11, write both
-//                    planes into a shared-memory ring in the UMMA MN-major / 128-byte-swizzle layout; per-stage
-//                    partial of b = sum r*y
-//   MMA warp       : one elected lane issues tcgen05.mma (kind::f16, M=64, N=64, K=16): D1 += hi hi^T,
-//                    D2 += hi lo^T + lo hi^T into TMEM; the Gramian is D1 + 2^-11 D2 (error-compensated split,
-//                    ~2^-22 relative: fp32-grade, needed for the 1e-4 parity target; plain fp16/tf32 is 2^-11);
-//                    lanes 0-15 fold the per-stage b partials in stage order (deterministic)
-//   epilogue warps : tcgen05.ld the accumulators (one TMEM lane quadrant per warp), add lambda*n_u on the
-//                    diagonal, hand the matrix to a solver warp through shared memory
-//   solver warps   : one warp per system, two matrix rows per lane in registers, right-looking Cholesky with the
-//                    pivot column broadcast through shared memory, forward substitution fused (augmented column),
-//                    butterfly back substitution; writes x_u
+// Data layout in HBM: besides the fp32 factor matrix every side keeps two fp16 "gather planes" hi = f16(x) and
+// lo = f16((x - hi) * 2^11) (64 halves = 128 B per row each).  hi + lo * 2^-11 carries ~22 mantissa bits, so
+// the Gramian  hi hi^T + 2^-11 (hi lo^T + lo hi^T)  is fp32-grade (plain fp16 / tf32 would be 2^-11: not enough
+// for the 1e-4 parity target) while every product is exact in the fp32 accumulator.
+//
+//   producer warp  : reads the CSR slice of 16 ratings (coalesced), issues TMA gather4 loads of the 16 partner
+//                    rows of both planes straight into the UMMA MN-major / 128-byte-swizzle stage (no registers, no
+//                    per-rating SM instructions), and writes the ratings as two extra 64-wide operand chunks
+//   MMA warp       : per stage two tcgen05.mma (kind::f16, M=64, K=16):
+//                        D[:,   0:192] (+)= hi [hi | lo | R ]^T        (N = 192)
+//                        D[:, 64:192]   += lo [hi |      R']^T        (N = 128, leading-dim offset skips `lo`)
+//                    => cols 0-63 hi hi^T, 64-127 hi lo^T + lo hi^T, col 128 sum r_hi*hi, col 129 the 2^-11 terms of
+//                    b = Y^T r.  Accumulators live in TMEM (2 slots x 256 columns).
+//   epilogue warps : tcgen05.ld one TMEM lane quadrant each, G = D1 + 2^-11 D2 (+ lambda n on the diagonal), b, and
+//                    hand the system to a solver warp through shared memory
+//   solver warps   : 8 warps, one system each: two matrix rows per lane in registers, right-looking Cholesky in 16
+//                    rank-4 panel steps (two loops, packed FFMA2, register window rotated inside the last update of
+//                    a panel), L columns kept in the hand-off buffer, fused forward substitution, column-sweep back
+//                    substitution; writes x_u (fp32) and its two gather planes.
 //
 // Takes over the FlinkML `updateFactors` coGroup body (entered from
 // flink-als/src/main/scala/de/tub/it4bi/ALSImpl.scala:52), same math as k_als_rows_generic (als_kernels.cu).
 // Algorithmic bytes per half-step: nnz*(4 idx + 4 val + 4*64 row) + N*(4 ptr + 4*64 out)  (SURVEY.md 8d).
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -24,28 +32,24 @@ namespace fms {
 namespace tc {
 
 constexpr int D = 64;
-constexpr int KROWS = 16;                         // gathered rows per stage == K of one tcgen05.mma (fp16)
-constexpr int TILE_BYTES = KROWS * 128;           // one plane (hi or lo) of one stage, 2 swizzle atoms
-constexpr int STAGE_BYTES = 2 * TILE_BYTES;
-constexpr int NSTG = 16;                          // ring depth (64 KB)
-constexpr int NACC = 4;                           // TMEM accumulator slots (128 columns each: D1 | D2)
-constexpr int NGB = 8;                            // Gramian hand-off buffers: two per solver warp
-constexpr int GLD = 68;                           // padded row pitch of a hand-off buffer (floats)
-constexpr int N_EPI = 4, N_SOLVE = 4, N_LOAD = 7; // warps per role (+1 MMA warp)
-constexpr int W_EPI0 = 0, W_SOLVE0 = 4, W_MMA = 8, W_LOAD0 = 9;
-constexpr int NWARPS = 16;
+constexpr int KROWS = 16;                         // ratings per stage == K of one tcgen05.mma (fp16)
+constexpr int TILE_BYTES = KROWS * 128;           // one 64-wide operand chunk of one stage (two swizzle atoms)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // hi | lo | R | R'
+constexpr int NSTG = 8;                           // ring depth (64 KB, 32 KB of gathers in flight)
+constexpr int NACC = 2;                           // TMEM accumulator slots of 256 columns
+constexpr int N_EPI = 4, N_SOLVE = 8;
+constexpr int NGB = N_SOLVE;                      // one hand-off / L buffer per solver warp
+constexpr int GLD = 68;                           // row pitch of a hand-off buffer (floats)
+constexpr int W_EPI0 = 0, W_SOLVE0 = 4, W_MMA = 12, W_PROD = 13;
+constexpr int NWARPS = 14;
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
-struct Smem {
-    // offsets in bytes from the 1024-aligned base
+struct Smem {   // byte offsets from the 1024-aligned base
     static constexpr int ring = 0;
-    static constexpr int bpart = ring + NSTG * STAGE_BYTES;                 // NSTG x 64 floats
-    static constexpr int gbuf = bpart + NSTG * D * 4;                       // NGB x 64 x GLD floats
-    static constexpr int bacc = gbuf + NGB * D * GLD * 4;                   // NACC x 64 floats (+ n)
-    static constexpr int bsol = bacc + NACC * (D + 4) * 4;                  // NGB x (64 floats + n + row)
-    static constexpr int colb = bsol + NGB * (D + 4) * 4;                   // N_SOLVE x 64 floats (1 / L_jj)
-    static constexpr int lring = colb + N_SOLVE * D * 4;                    // N_LOAD x 4 x 32 words (index ring)
-    static constexpr int bars = lring + N_LOAD * 4 * 32 * 4;                // mbarriers
+    static constexpr int gbuf = ring + NSTG * STAGE_BYTES;                  // NGB x 64 x GLD floats
+    static constexpr int bsol = gbuf + NGB * D * GLD * 4;                   // NGB x 64 floats (rhs)
+    static constexpr int invd = bsol + NGB * D * 4;                         // N_SOLVE x 64 floats (1 / L_jj)
+    static constexpr int bars = invd + N_SOLVE * D * 4;
     static constexpr int n_bars = 2 * NSTG + 2 * NACC + 2 * NGB;
     static constexpr int tmem_ptr = bars + n_bars * 8;
     static constexpr int total = tmem_ptr + 16;
@@ -58,53 +62,62 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes instead of spinning
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(ok)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(1000000u)
             : "memory");
     } while (!ok);
-}
-// long waits (epilogue / solver hand-offs): back off so the spinning warp does not eat issue slots
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    for (;;) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) break;
-        __nanosleep(100);
-    }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+
+// TMA gather4: four rows (row indices r0..r3, 64 halves each) of a 2-D fp16 tensor -> 512 contiguous swizzled bytes
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *map, uint32_t bar, int r0, int r1, int r2, int r3) {
     asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
         : "memory");
 }
+
+// One stage worth of tensor-core work, issued by one elected lane without a divergent branch.
+//   d       : TMEM address of the accumulator slot (column 0)
+//   a_hi/lo : descriptors of the hi / lo chunks as A operand (M = 64)
+//   b3      : descriptor hi|lo|R  (three chunks, leading-dim offset one chunk)
+//   b2      : descriptor hi|R'    (two chunks, leading-dim offset three chunks)
+__device__ __forceinline__ void tc_stage_mma(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b3, uint64_t b2, uint32_t idesc192,
+                                             uint32_t idesc128, uint32_t accumulate, uint32_t bar_empty, uint32_t bar_acc, uint32_t last) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pa, pl, pt;\n"
+        ".reg .b32 d2;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pa, %6, 0;\n"
+        "setp.ne.b32 pt, %9, 0;\n"
+        "and.pred pl, pt, pe;\n"
+        "setp.eq.u32 pt, %0, %0;\n"
+        "add.u32 d2, %0, 64;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %4, pa;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [d2], %2, %10, %5, pt;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
+        "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n"
+        "}\n" ::"r"(d),
+        "l"(a_hi), "l"(a_lo), "l"(b3), "r"(idesc192), "r"(idesc128), "r"(accumulate), "r"(bar_empty), "r"(bar_acc), "r"(last), "l"(b2)
+        : "memory");
+}
+
 // 32 lanes x 32 columns of 32-bit: thread i of the warp reads TMEM lane (quadrant base + i), columns [c, c+32)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -122,30 +135,81 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld2(uint32_t taddr, float &a, float &b) {
+    uint32_t r0, r1;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    a = __uint_as_float(r0);
+    b = __uint_as_float(r1);
+}
 
-// UMMA shared-memory descriptor: MN-major, SWIZZLE_128B, 16 K-rows of 128 B (two 8-row atoms, SBO = 1024 B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+// UMMA shared-memory descriptor: MN-major, SWIZZLE_128B; K = 16 rows = two 8-row atoms (stride 1024 B); successive
+// 64-wide MN chunks are `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);            // start address
-    d |= (uint64_t)((TILE_BYTES >> 4) & 0x3FFF) << 16;     // leading byte offset (next 64-wide MN chunk; unused: one chunk)
-    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;           // stride byte offset: next group of 8 K-rows
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
     return d;
 }
-// instruction descriptor: D=f32, A=B=f16, both MN-major, N=64, M=64
-constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((64u >> 4) << 24);
+// instruction descriptor: D = f32, A = B = f16, both MN-major, M = 64
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((64u >> 4) << 24);
+}
 
 __device__ __forceinline__ float rsqrt_refined(float x) {
     float r = rsqrtf(x);
     return r * fmaf(-0.5f * x * r, r, 1.5f);              // one Newton step: ~1 ulp
 }
+__device__ __forceinline__ void split_half(float x, __half &hi, __half &lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * LO_SCALE);
+}
+
+// 4x4 Cholesky of the pivot block + forward substitution of the panel's rhs (redundantly in every lane)
+struct Panel {
+    float i0, i1, i2, i3, l10, l20, l30, l21, l31, l32, z0, z1, z2, z3;
+    bool bad;
+};
+__device__ __forceinline__ Panel panel_factor(float d00, float d10, float d11, float d20, float d21, float d22, float d30, float d31,
+                                              float d32, float d33, float zb0, float zb1, float zb2, float zb3) {
+    Panel p;
+    p.bad = !(d00 > 0.f);
+    p.i0 = rsqrt_refined(d00);
+    p.l10 = d10 * p.i0; p.l20 = d20 * p.i0; p.l30 = d30 * p.i0;
+    const float t11 = fmaf(-p.l10, p.l10, d11);
+    p.bad |= !(t11 > 0.f);
+    p.i1 = rsqrt_refined(t11);
+    p.l21 = fmaf(-p.l20, p.l10, d21) * p.i1; p.l31 = fmaf(-p.l30, p.l10, d31) * p.i1;
+    const float t22 = fmaf(-p.l21, p.l21, fmaf(-p.l20, p.l20, d22));
+    p.bad |= !(t22 > 0.f);
+    p.i2 = rsqrt_refined(t22);
+    p.l32 = fmaf(-p.l31, p.l21, fmaf(-p.l30, p.l20, d32)) * p.i2;
+    const float t33 = fmaf(-p.l32, p.l32, fmaf(-p.l31, p.l31, fmaf(-p.l30, p.l30, d33)));
+    p.bad |= !(t33 > 0.f);
+    p.i3 = rsqrt_refined(t33);
+    p.z0 = zb0 * p.i0;
+    p.z1 = fmaf(-p.z0, p.l10, zb1) * p.i1;
+    p.z2 = fmaf(-p.z1, p.l21, fmaf(-p.z0, p.l20, zb2)) * p.i2;
+    p.z3 = fmaf(-p.z2, p.l32, fmaf(-p.z1, p.l31, fmaf(-p.z0, p.l30, zb3))) * p.i3;
+    return p;
+}
+// one matrix row against the factored pivot block: x = a * Ld^-T
+__device__ __forceinline__ void panel_row(const Panel &p, float a0, float a1, float a2, float a3, float &x0, float &x1, float &x2, float &x3) {
+    x0 = a0 * p.i0;
+    x1 = fmaf(-x0, p.l10, a1) * p.i1;
+    x2 = fmaf(-x1, p.l21, fmaf(-x0, p.l20, a2)) * p.i2;
+    x3 = fmaf(-x2, p.l32, fmaf(-x1, p.l31, fmaf(-x0, p.l30, a3))) * p.i3;
+}
 
 template <bool DUMP>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
-    const int64_t *__restrict__ ptr, const int32_t *__restrict__ col, const float *__restrict__ val,
-    const float *__restrict__ P, float *__restrict__ T, float lambda, int64_t row_begin, int64_t row_end,
-    int *__restrict__ info, float *__restrict__ dump) {
+    const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const int64_t *__restrict__ ptr,
+    const int32_t *__restrict__ col, const float *__restrict__ val, float *__restrict__ T, __half *__restrict__ T_hi,
+    __half *__restrict__ T_lo, int zero_row, float lambda, int64_t row_begin, int64_t row_end, int *__restrict__ info,
+    float *__restrict__ dump) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
     const uint32_t sm_base = smem_u32(sm);
@@ -159,9 +223,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
     auto bar_g_empty = [&](int g) { return bar0 + 8u * (2 * NSTG + 2 * NACC + NGB + g); };
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sm + Smem::tmem_ptr);
 
+    // zero the ring once: the R / R' chunks only ever get their first four bytes per row rewritten
+    for (int i = threadIdx.x; i < NSTG * STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(sm + Smem::ring)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTG; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-        for (int a = 0; a < NACC; ++a) { mbar_init(bar_acc_full(a), 2); mbar_init(bar_acc_empty(a), N_EPI); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(bar_acc_full(a), 1); mbar_init(bar_acc_empty(a), N_EPI); }
         for (int g = 0; g < NGB; ++g) { mbar_init(bar_g_full(g), N_EPI); mbar_init(bar_g_empty(g), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -169,6 +235,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sm_base + Smem::tmem_ptr) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    fence_proxy_async();                                           // the zero fill must be visible to the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -177,155 +244,83 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
     const int64_t first = row_begin + blockIdx.x;
     const int64_t stride = gridDim.x;
 
-    if (warp >= W_LOAD0) {
-        // ================================================================== loaders
-        // Loader warp lw owns the CTA's stages lw, lw + N_LOAD, ...  Three-deep software pipeline per warp:
-        //   index  (IA stages ahead): lanes 0-15 read col/val of the stage's 16 ratings, park them in a small
-        //                              shared ring and prefetch the partner rows into L2
-        //   gather (1 stage ahead)   : 8 x LDG.128 per lane into one of two register buffers
-        //   convert (current)        : fp32 -> fp16 hi / lo planes in UMMA layout, b partial, signal the MMA warp
-        const int lw = warp - W_LOAD0;
-        const int half = lane >> 4, sub = lane & 15;
-        const float4 *P4 = reinterpret_cast<const float4 *>(P);
-        constexpr int IA = 3, IRING = 4;
-        int *iring = reinterpret_cast<int *>(sm + Smem::lring + lw * IRING * 32 * 4);   // [IRING][16 idx | 16 rating bits]
-
-        struct It { int64_t row, s0, e0; uint32_t base, nst; };
-        auto it_init = [&](It &it) {
-            it.row = first; it.base = 0; it.nst = 0; it.s0 = it.e0 = 0;
-            if (it.row < row_end) { it.s0 = ptr[it.row]; it.e0 = ptr[it.row + 1]; it.nst = (uint32_t)((it.e0 - it.s0 + KROWS - 1) / KROWS); }
-        };
-        // position the iterator on global stage counter c; false when the CTA has no such stage
-        auto it_seek = [&](It &it, uint32_t c) -> bool {
-            while (it.row < row_end && c >= it.base + it.nst) {
-                it.base += it.nst;
-                it.row += stride;
-                if (it.row < row_end) { it.s0 = ptr[it.row]; it.e0 = ptr[it.row + 1]; it.nst = (uint32_t)((it.e0 - it.s0 + KROWS - 1) / KROWS); }
+    if (warp == W_PROD) {
+        // ================================================================== producer: CSR slice -> TMA gather4 + rating chunks
+        int64_t row = first, s0 = 0, e0 = 0;
+        uint32_t base = 0, nst = 0;                                // stage counters of the current row
+        auto load_row = [&]() { s0 = ptr[row]; e0 = ptr[row + 1]; nst = (uint32_t)((e0 - s0 + KROWS - 1) / KROWS); };
+        if (row < row_end) load_row();
+        // index / rating registers of the stage being issued and the two after it (lanes 0..15 hold one rating each)
+        int idx0 = zero_row, idx1 = zero_row, idx2 = zero_row;
+        float rt0 = 0.f, rt1 = 0.f, rt2 = 0.f;
+        bool ok0 = false, ok1 = false, ok2 = false;
+        auto fetch = [&](uint32_t c, int &idx, float &rt) -> bool {   // positions (row, base, ...) on stage c, loads its slice
+            while (row < row_end && c >= base + nst) {
+                base += nst;
+                row += stride;
+                if (row < row_end) load_row();
             }
-            return it.row < row_end;
-        };
-        It it_i, it_g;
-        it_init(it_i); it_init(it_g);
-
-        auto do_index = [&](uint32_t n) {
-            const uint32_t c = (uint32_t)lw + n * N_LOAD;
-            if (!it_seek(it_i, c)) return;
-            const int64_t k = it_i.s0 + (int64_t)(c - it_i.base) * KROWS + sub;
-            if (half == 0) {
-                const bool ok = k < it_i.e0;
-                const int32_t ci = ok ? col[k] : -1;
-                const float rv = ok ? val[k] : 0.f;
-                int *slot = iring + (n % IRING) * 32;
-                const int pos = (sub & 1) * 8 + (sub >> 1);       // rows of one half-warp become contiguous
-                slot[pos] = ci;
-                slot[16 + pos] = __float_as_int(rv);
-                if (ok) {
-                    const char *rp = reinterpret_cast<const char *>(P + (int64_t)ci * D);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 128));
-                }
-            }
-        };
-        auto do_gather = [&](uint32_t n, float4 (&v)[8], float (&rt)[8]) -> bool {
-            const uint32_t c = (uint32_t)lw + n * N_LOAD;
-            if (!it_seek(it_g, c)) return false;
-            __syncwarp();                                          // ring entries written by lanes 0-15 of this warp
-            const int *slot = iring + (n % IRING) * 32;
-            const int4 i0 = *reinterpret_cast<const int4 *>(slot + half * 8), i1 = *reinterpret_cast<const int4 *>(slot + half * 8 + 4);
-            const int4 r0 = *reinterpret_cast<const int4 *>(slot + 16 + half * 8), r1 = *reinterpret_cast<const int4 *>(slot + 16 + half * 8 + 4);
-            const int ci[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-            const int ri[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                rt[i] = __int_as_float(ri[i]);
-                v[i] = ci[i] >= 0 ? P4[(int64_t)ci[i] * (D / 4) + sub] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            if (row >= row_end) { idx = zero_row; rt = 0.f; return false; }
+            const int64_t k = s0 + (int64_t)(c - base) * KROWS + (lane & 15);
+            const bool in = k < e0;
+            idx = in ? col[k] : zero_row;
+            rt = in ? val[k] : 0.f;
             return true;
         };
-        auto do_convert = [&](uint32_t n, const float4 (&v)[8], const float (&rt)[8]) {
-            const uint32_t c = (uint32_t)lw + n * N_LOAD;
+        ok0 = fetch(0, idx0, rt0);
+        ok1 = ok0 ? fetch(1, idx1, rt1) : false;
+        ok2 = ok1 ? fetch(2, idx2, rt2) : false;
+        for (uint32_t c = 0; ok0; ++c) {
             const int slot = c % NSTG;
+            const uint32_t stage = sm_base + Smem::ring + slot * STAGE_BYTES;
             mbar_wait(bar_empty(slot), ((c / NSTG) & 1) ^ 1);
-            unsigned char *hi_t = sm + Smem::ring + slot * STAGE_BYTES;
-            unsigned char *lo_t = hi_t + TILE_BYTES;
-            float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = 2 * i + half;
-                bp.x = fmaf(rt[i], v[i].x, bp.x); bp.y = fmaf(rt[i], v[i].y, bp.y);
-                bp.z = fmaf(rt[i], v[i].z, bp.z); bp.w = fmaf(rt[i], v[i].w, bp.w);
-                const __half2 h01 = __floats2half2_rn(v[i].x, v[i].y), h23 = __floats2half2_rn(v[i].z, v[i].w);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                const __half2 l01 = __floats2half2_rn((v[i].x - f01.x) * LO_SCALE, (v[i].y - f01.y) * LO_SCALE);
-                const __half2 l23 = __floats2half2_rn((v[i].z - f23.x) * LO_SCALE, (v[i].w - f23.y) * LO_SCALE);
-                // 128-byte swizzle: 16-byte chunk index ^= row & 7 (tiles are 1024-byte aligned)
-                const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)sub >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)sub & 1u) * 8u;
-                uint2 hv, lv;
-                hv.x = *reinterpret_cast<const uint32_t *>(&h01); hv.y = *reinterpret_cast<const uint32_t *>(&h23);
-                lv.x = *reinterpret_cast<const uint32_t *>(&l01); lv.y = *reinterpret_cast<const uint32_t *>(&l23);
-                *reinterpret_cast<uint2 *>(hi_t + off) = hv;
-                *reinterpret_cast<uint2 *>(lo_t + off) = lv;
+            // ratings: R row r = (r_hi, r_lo * 2^11, 0...), R' row r = (0, r_hi, 0...); 16-byte chunk 0 sits at chunk (r & 7)
+            if (lane < 16) {
+                __half rh, rl;
+                split_half(rt0, rh, rl);
+                const uint32_t off = (uint32_t)lane * 128u + (((uint32_t)lane & 7u) << 4);
+                const uint32_t w0 = (uint32_t)__half_as_ushort(rh) | ((uint32_t)__half_as_ushort(rl) << 16);
+                const uint32_t w1 = (uint32_t)__half_as_ushort(rh) << 16;
+                *reinterpret_cast<uint32_t *>(sm + Smem::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + off) = w0;
+                *reinterpret_cast<uint32_t *>(sm + Smem::ring + slot * STAGE_BYTES + 3 * TILE_BYTES + off) = w1;
             }
-            bp.x += __shfl_xor_sync(0xffffffffu, bp.x, 16); bp.y += __shfl_xor_sync(0xffffffffu, bp.y, 16);
-            bp.z += __shfl_xor_sync(0xffffffffu, bp.z, 16); bp.w += __shfl_xor_sync(0xffffffffu, bp.w, 16);
-            if (half == 0) reinterpret_cast<float4 *>(sm + Smem::bpart + slot * D * 4)[sub] = bp;
-            fence_proxy_async();                                  // generic-proxy stores -> visible to the tensor core
+            fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full(slot));
-        };
-
-        float4 va[8], vb[8];
-        float ra[8], rb[8];
-        for (uint32_t n = 0; n < IA; ++n) do_index(n);
-        bool have_a = do_gather(0, va, ra), have_b = false;
-        for (uint32_t n = 0; have_a; n += 2) {
-            do_index(n + IA);
-            have_b = do_gather(n + 1, vb, rb);
-            do_convert(n, va, ra);
-            if (!have_b) break;
-            do_index(n + 1 + IA);
-            have_a = do_gather(n + 2, va, ra);
-            do_convert(n + 1, vb, rb);
+            if (lane == 0) mbar_expect_tx(bar_full(slot), 2 * TILE_BYTES);
+            __syncwarp();
+            // lane t (0..3) gathers rows 4t..4t+3 of both planes
+            const int g = (lane & 3) * 4;
+            const int r0 = __shfl_sync(0xffffffffu, idx0, g), r1 = __shfl_sync(0xffffffffu, idx0, g + 1);
+            const int r2 = __shfl_sync(0xffffffffu, idx0, g + 2), r3 = __shfl_sync(0xffffffffu, idx0, g + 3);
+            if (lane < 4) {
+                tma_gather4(stage + lane * 512, &map_hi, bar_full(slot), r0, r1, r2, r3);
+                tma_gather4(stage + TILE_BYTES + lane * 512, &map_lo, bar_full(slot), r0, r1, r2, r3);
+            }
+            // rotate the prefetch registers, fetch the slice three stages ahead
+            idx0 = idx1; rt0 = rt1; ok0 = ok1;
+            idx1 = idx2; rt1 = rt2; ok1 = ok2;
+            ok2 = ok1 ? fetch(c + 3, idx2, rt2) : false;
         }
     } else if (warp == W_MMA) {
-        // ================================================================== MMA issuer (+ b reduction on lanes 0-15)
+        // ================================================================== MMA issuer
         uint32_t stage_ctr = 0, job = 0;
+        const uint32_t id192 = make_idesc(192), id128 = make_idesc(128);
         for (int64_t row = first; row < row_end; row += stride, ++job) {
             const int64_t s0 = ptr[row], e0 = ptr[row + 1];
             const int nst = (int)((e0 - s0 + KROWS - 1) / KROWS);
             const int acc = job % NACC;
             mbar_wait(bar_acc_empty(acc), ((job / NACC) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t d1 = tmem_base + (uint32_t)acc * 128u, d2 = d1 + 64u;
-            float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t d = tmem_base + (uint32_t)acc * 256u;
             for (int st = 0; st < nst; ++st, ++stage_ctr) {
                 const int slot = stage_ctr % NSTG;
                 mbar_wait(bar_full(slot), (stage_ctr / NSTG) & 1);
                 tc_fence_after();
-                if (lane < 16) {
-                    const float4 p = reinterpret_cast<const float4 *>(sm + Smem::bpart + slot * D * 4)[lane];
-                    bsum.x += p.x; bsum.y += p.y; bsum.z += p.z; bsum.w += p.w;
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    const uint32_t hi_a = sm_base + Smem::ring + slot * STAGE_BYTES;
-                    const uint64_t dh = make_desc(hi_a), dl = make_desc(hi_a + TILE_BYTES);
-                    tc_mma_f16(d1, dh, dh, IDESC, st > 0 ? 1u : 0u);      // D1 (+)= hi hi^T
-                    tc_mma_f16(d2, dh, dl, IDESC, st > 0 ? 1u : 0u);      // D2 (+)= hi lo^T
-                    tc_mma_f16(d2, dl, dh, IDESC, 1u);                    // D2  += lo hi^T
-                    tc_commit(bar_empty(slot));                           // ring slot free once these MMAs retire
-                }
-                __syncwarp();
+                const uint32_t hi_a = sm_base + Smem::ring + slot * STAGE_BYTES;
+                tc_stage_mma(d, make_desc(hi_a, TILE_BYTES), make_desc(hi_a + TILE_BYTES, TILE_BYTES), make_desc(hi_a, TILE_BYTES),
+                             make_desc(hi_a, 3 * TILE_BYTES), id192, id128, st > 0 ? 1u : 0u, bar_empty(slot), bar_acc_full(acc),
+                             st == nst - 1 ? 1u : 0u);
             }
-            float *bo = reinterpret_cast<float *>(sm + Smem::bacc + acc * (D + 4) * 4);
-            if (lane < 16) reinterpret_cast<float4 *>(bo)[lane] = bsum;
-            if (lane == 16) { bo[D] = (float)(e0 - s0); reinterpret_cast<int *>(bo)[D + 1] = (int)(row - row_begin); }
-            __syncwarp();
-            if (lane == 0) {
-                tc_commit(bar_acc_full(acc));                             // arrives when every MMA of this row has retired
-                mbar_arrive(bar_acc_full(acc));                           // releases the b / n stores above
-            }
-            __syncwarp();
         }
     } else if (warp < W_SOLVE0) {
         // ================================================================== epilogue: TMEM -> registers -> hand-off buffer
@@ -333,15 +328,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
         uint32_t job = 0;
         for (int64_t row = first; row < row_end; row += stride, ++job) {
             const int acc = job % NACC, g = job % NGB;
+            const float reg = lambda * (float)(ptr[row + 1] - ptr[row]);
             mbar_wait(bar_acc_full(acc), (job / NACC) & 1);
             tc_fence_after();
             mbar_wait(bar_g_empty(g), ((job / NGB) & 1) ^ 1);
-            const float *bi = reinterpret_cast<const float *>(sm + Smem::bacc + acc * (D + 4) * 4);
-            float *bo = reinterpret_cast<float *>(sm + Smem::bsol + g * (D + 4) * 4);
+            float *bo = reinterpret_cast<float *>(sm + Smem::bsol + g * D * 4);
             float *G = reinterpret_cast<float *>(sm + Smem::gbuf + g * D * GLD * 4);
-            const float reg = lambda * bi[D];
             const int my_row = 16 * q + lane;                     // valid for lane < 16
-            const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * 128u;
+            const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * 256u;
 #pragma unroll
             for (int c0 = 0; c0 < D; c0 += 32) {
                 float d1[32], d2[32];
@@ -362,31 +356,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                     }
                 }
             }
-            if (q == 0) {
-                bo[lane] = bi[lane]; bo[lane + 32] = bi[lane + 32];
-                if (lane < 2) bo[D + lane] = bi[D + lane];
-            }
+            float b_hi, b_lo;
+            tc_ld2(tq + 128, b_hi, b_lo);
+            if (lane < 16) bo[my_row] = fmaf(b_lo, LO_INV, b_hi);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar_acc_empty(acc)); mbar_arrive(bar_g_full(g)); }
         }
-    } else {
+    } else if (warp < W_MMA) {
         // ================================================================== solvers: one warp per system
-        // Lane l owns matrix rows l and l+32 in registers.  Right-looking Cholesky in 16 rank-4 panel steps written as
-        // two LOOPS (panels over columns 0..31, then 32..63) so the code stays instruction-cache resident: the
-        // register window is rotated by 4 columns per panel (folded into the last FFMA2 of the panel, no moves).
-        // The finished L columns go back into the hand-off buffer (column-major, pitch GLD) where the trailing
-        // updates (broadcast LDS.128 + packed FFMA2) and the back substitution read them.  Forward substitution is
-        // fused (b is carried as an extra column).
         const int sv = warp - W_SOLVE0;
-        float *invd = reinterpret_cast<float *>(sm + Smem::colb + sv * D * 4);
-        uint32_t job = 0;
+        const int g = sv;
+        float *invd = reinterpret_cast<float *>(sm + Smem::invd + sv * D * 4);
+        float *G = reinterpret_cast<float *>(sm + Smem::gbuf + g * D * GLD * 4);
+        const float *bi = reinterpret_cast<const float *>(sm + Smem::bsol + g * D * 4);
+        uint32_t job = 0, use = 0;
         for (int64_t row = first; row < row_end; row += stride, ++job) {
             if ((int)(job % N_SOLVE) != sv) continue;
-            const int g = job % NGB;
-            mbar_wait_sleep(bar_g_full(g), (job / NGB) & 1);
-            float *G = reinterpret_cast<float *>(sm + Smem::gbuf + g * D * GLD * 4);
-            const float *bi = reinterpret_cast<const float *>(sm + Smem::bsol + g * (D + 4) * 4);
+            mbar_wait(bar_g_full(g), use & 1);
+            ++use;
             float2 A0[16], A1a[16], A1b[16];                      // row l cols 0..31 | row l+32 cols 0..31 | row l+32 cols 32..63
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -418,62 +406,35 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                 const float d32 = __shfl_sync(0xffffffffu, A0[1].x, j0 + 3), d33 = __shfl_sync(0xffffffffu, A0[1].y, j0 + 3);
                 const float zb0 = __shfl_sync(0xffffffffu, b0, j0), zb1 = __shfl_sync(0xffffffffu, b0, j0 + 1);
                 const float zb2 = __shfl_sync(0xffffffffu, b0, j0 + 2), zb3 = __shfl_sync(0xffffffffu, b0, j0 + 3);
-                // 4x4 Cholesky of the diagonal block, redundantly in every lane
-                bad |= !(d00 > 0.f);
-                const float i0 = rsqrt_refined(d00);
-                const float l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
-                const float t11 = fmaf(-l10, l10, d11);
-                bad |= !(t11 > 0.f);
-                const float i1 = rsqrt_refined(t11);
-                const float l21 = fmaf(-l20, l10, d21) * i1, l31 = fmaf(-l30, l10, d31) * i1;
-                const float t22 = fmaf(-l21, l21, fmaf(-l20, l20, d22));
-                bad |= !(t22 > 0.f);
-                const float i2 = rsqrt_refined(t22);
-                const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, d32)) * i2;
-                const float t33 = fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, d33)));
-                bad |= !(t33 > 0.f);
-                const float i3 = rsqrt_refined(t33);
-                // forward substitution for the panel's right-hand side
-                const float z0 = zb0 * i0;
-                const float z1 = fmaf(-z0, l10, zb1) * i1;
-                const float z2 = fmaf(-z1, l21, fmaf(-z0, l20, zb2)) * i2;
-                const float z3 = fmaf(-z2, l32, fmaf(-z1, l31, fmaf(-z0, l30, zb3))) * i3;
-                // my two rows of the panel: x = A[i][J] * Ld^-T
-                const float p0 = A0[0].x * i0;
-                const float p1 = fmaf(-p0, l10, A0[0].y) * i1;
-                const float p2 = fmaf(-p1, l21, fmaf(-p0, l20, A0[1].x)) * i2;
-                const float p3 = fmaf(-p2, l32, fmaf(-p1, l31, fmaf(-p0, l30, A0[1].y))) * i3;
-                const float q0 = A1a[0].x * i0;
-                const float q1 = fmaf(-q0, l10, A1a[0].y) * i1;
-                const float q2 = fmaf(-q1, l21, fmaf(-q0, l20, A1a[1].x)) * i2;
-                const float q3 = fmaf(-q2, l32, fmaf(-q1, l31, fmaf(-q0, l30, A1a[1].y))) * i3;
-                // right-hand side: rows below the panel get b_i -= sum_c L[i][c] z_c; pivot rows keep z
-                const float nb0 = fmaf(-p3, z3, fmaf(-p2, z2, fmaf(-p1, z1, fmaf(-p0, z0, b0))));
-                b1 = fmaf(-q3, z3, fmaf(-q2, z2, fmaf(-q1, z1, fmaf(-q0, z0, b1))));
+                const Panel P = panel_factor(d00, d10, d11, d20, d21, d22, d30, d31, d32, d33, zb0, zb1, zb2, zb3);
+                bad |= P.bad;
+                float p0, p1, p2, p3, q0, q1, q2, q3;
+                panel_row(P, A0[0].x, A0[0].y, A0[1].x, A0[1].y, p0, p1, p2, p3);
+                panel_row(P, A1a[0].x, A1a[0].y, A1a[1].x, A1a[1].y, q0, q1, q2, q3);
+                // rhs: rows below the panel get b_i -= sum_c L[i][c] z_c; pivot rows keep z; finished rows keep theirs
+                const float nb0 = fmaf(-p3, P.z3, fmaf(-p2, P.z2, fmaf(-p1, P.z1, fmaf(-p0, P.z0, b0))));
+                b1 = fmaf(-q3, P.z3, fmaf(-q2, P.z2, fmaf(-q1, P.z1, fmaf(-q0, P.z0, b1))));
                 const int rel = lane - j0;
-                b0 = rel == 0 ? z0 : rel == 1 ? z1 : rel == 2 ? z2 : rel == 3 ? z3 : rel > 3 ? nb0 : b0;   // finished rows keep z
+                b0 = rel == 0 ? P.z0 : rel == 1 ? P.z1 : rel == 2 ? P.z2 : rel == 3 ? P.z3 : rel > 3 ? nb0 : b0;
                 // publish the four L columns (column-major) and 1 / L_jj
                 float *Lc = Ls + j0 * GLD;
                 Lc[lane] = p0; Lc[GLD + lane] = p1; Lc[2 * GLD + lane] = p2; Lc[3 * GLD + lane] = p3;
                 Lc[lane + 32] = q0; Lc[GLD + lane + 32] = q1; Lc[2 * GLD + lane + 32] = q2; Lc[3 * GLD + lane + 32] = q3;
-                if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(i0, i1, i2, i3);
+                if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(P.i0, P.i1, P.i2, P.i3);
                 __syncwarp();
-                // trailing update; the window (positions 2..15 = columns j0+4..j0+31) shifts down by two float2
+                // trailing update.  Window positions 2..15 (columns j0+4 .. j0+31) are updated in place for the first
+                // three panel columns; the fourth update writes two positions down, which rotates the window for free.
                 const float pm[4] = {-p0, -p1, -p2, -p3}, qm[4] = {-q0, -q1, -q2, -q3};
-                float2 N0[16], N1[16];
 #pragma unroll
-                for (int w = 0; w < 14; ++w) { N0[w] = A0[w + 2]; N1[w] = A1a[w + 2]; }
-                N0[14] = N0[15] = N1[14] = N1[15] = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 3; ++c) {
                     const float2 pp = make_float2(pm[c], pm[c]), qq = make_float2(qm[c], qm[c]);
                     const float *col_c = Lc + c * GLD + j0 + 4;                       // L[j0+4 ..][j0+c]
 #pragma unroll
                     for (int w4 = 0; w4 < 7; ++w4) {
                         const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
                         const float2 la = make_float2(lv.x, lv.y), lb = make_float2(lv.z, lv.w);
-                        N0[2 * w4] = __ffma2_rn(pp, la, N0[2 * w4]); N0[2 * w4 + 1] = __ffma2_rn(pp, lb, N0[2 * w4 + 1]);
-                        N1[2 * w4] = __ffma2_rn(qq, la, N1[2 * w4]); N1[2 * w4 + 1] = __ffma2_rn(qq, lb, N1[2 * w4 + 1]);
+                        A0[2 + 2 * w4] = __ffma2_rn(pp, la, A0[2 + 2 * w4]); A0[3 + 2 * w4] = __ffma2_rn(pp, lb, A0[3 + 2 * w4]);
+                        A1a[2 + 2 * w4] = __ffma2_rn(qq, la, A1a[2 + 2 * w4]); A1a[3 + 2 * w4] = __ffma2_rn(qq, lb, A1a[3 + 2 * w4]);
                     }
                     const float *col_s = Lc + c * GLD + 32;                           // L[32 ..][j0+c]
 #pragma unroll
@@ -483,8 +444,24 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                         A1b[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A1b[2 * w4 + 1]);
                     }
                 }
+                {
+                    const float2 pp = make_float2(pm[3], pm[3]), qq = make_float2(qm[3], qm[3]);
+                    const float *col_c = Lc + 3 * GLD + j0 + 4;
 #pragma unroll
-                for (int w = 0; w < 16; ++w) { A0[w] = N0[w]; A1a[w] = N1[w]; }
+                    for (int w4 = 0; w4 < 7; ++w4) {
+                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
+                        const float2 la = make_float2(lv.x, lv.y), lb = make_float2(lv.z, lv.w);
+                        A0[2 * w4] = __ffma2_rn(pp, la, A0[2 + 2 * w4]); A0[2 * w4 + 1] = __ffma2_rn(pp, lb, A0[3 + 2 * w4]);
+                        A1a[2 * w4] = __ffma2_rn(qq, la, A1a[2 + 2 * w4]); A1a[2 * w4 + 1] = __ffma2_rn(qq, lb, A1a[3 + 2 * w4]);
+                    }
+                    const float *col_s = Lc + 3 * GLD + 32;
+#pragma unroll
+                    for (int w4 = 0; w4 < 8; ++w4) {
+                        const float4 lv = *reinterpret_cast<const float4 *>(col_s + 4 * w4);
+                        A1b[2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A1b[2 * w4]);
+                        A1b[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A1b[2 * w4 + 1]);
+                    }
+                }
             }
             // ---------------- panels over columns 32..63 (pivot rows live in A1b / b1 of lanes j0-32 .. +3)
 #pragma unroll 1
@@ -498,54 +475,40 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                 const float d32 = __shfl_sync(0xffffffffu, A1b[1].x, src + 3), d33 = __shfl_sync(0xffffffffu, A1b[1].y, src + 3);
                 const float zb0 = __shfl_sync(0xffffffffu, b1, src), zb1 = __shfl_sync(0xffffffffu, b1, src + 1);
                 const float zb2 = __shfl_sync(0xffffffffu, b1, src + 2), zb3 = __shfl_sync(0xffffffffu, b1, src + 3);
-                bad |= !(d00 > 0.f);
-                const float i0 = rsqrt_refined(d00);
-                const float l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
-                const float t11 = fmaf(-l10, l10, d11);
-                bad |= !(t11 > 0.f);
-                const float i1 = rsqrt_refined(t11);
-                const float l21 = fmaf(-l20, l10, d21) * i1, l31 = fmaf(-l30, l10, d31) * i1;
-                const float t22 = fmaf(-l21, l21, fmaf(-l20, l20, d22));
-                bad |= !(t22 > 0.f);
-                const float i2 = rsqrt_refined(t22);
-                const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, d32)) * i2;
-                const float t33 = fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, d33)));
-                bad |= !(t33 > 0.f);
-                const float i3 = rsqrt_refined(t33);
-                const float z0 = zb0 * i0;
-                const float z1 = fmaf(-z0, l10, zb1) * i1;
-                const float z2 = fmaf(-z1, l21, fmaf(-z0, l20, zb2)) * i2;
-                const float z3 = fmaf(-z2, l32, fmaf(-z1, l31, fmaf(-z0, l30, zb3))) * i3;
-                const float q0 = A1b[0].x * i0;
-                const float q1 = fmaf(-q0, l10, A1b[0].y) * i1;
-                const float q2 = fmaf(-q1, l21, fmaf(-q0, l20, A1b[1].x)) * i2;
-                const float q3 = fmaf(-q2, l32, fmaf(-q1, l31, fmaf(-q0, l30, A1b[1].y))) * i3;
-                const float nb1 = fmaf(-q3, z3, fmaf(-q2, z2, fmaf(-q1, z1, fmaf(-q0, z0, b1))));
+                const Panel P = panel_factor(d00, d10, d11, d20, d21, d22, d30, d31, d32, d33, zb0, zb1, zb2, zb3);
+                bad |= P.bad;
+                float q0, q1, q2, q3;
+                panel_row(P, A1b[0].x, A1b[0].y, A1b[1].x, A1b[1].y, q0, q1, q2, q3);
+                const float nb1 = fmaf(-q3, P.z3, fmaf(-q2, P.z2, fmaf(-q1, P.z1, fmaf(-q0, P.z0, b1))));
                 const int rel = lane - src;
-                b1 = rel == 0 ? z0 : rel == 1 ? z1 : rel == 2 ? z2 : rel == 3 ? z3 : rel > 3 ? nb1 : b1;
+                b1 = rel == 0 ? P.z0 : rel == 1 ? P.z1 : rel == 2 ? P.z2 : rel == 3 ? P.z3 : rel > 3 ? nb1 : b1;
                 float *Lc = Ls + j0 * GLD;
                 Lc[lane + 32] = q0; Lc[GLD + lane + 32] = q1; Lc[2 * GLD + lane + 32] = q2; Lc[3 * GLD + lane + 32] = q3;
-                if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(i0, i1, i2, i3);
+                if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(P.i0, P.i1, P.i2, P.i3);
                 __syncwarp();
                 const float qm[4] = {-q0, -q1, -q2, -q3};
-                float2 N1[16];
+                // columns beyond 63 read the neighbouring L column / padding: finite garbage that is never used
 #pragma unroll
-                for (int w = 0; w < 14; ++w) N1[w] = A1b[w + 2];
-                N1[14] = N1[15] = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 3; ++c) {
                     const float2 qq = make_float2(qm[c], qm[c]);
                     const float *col_c = Lc + c * GLD + j0 + 4;
 #pragma unroll
                     for (int w4 = 0; w4 < 7; ++w4) {
-                        // columns beyond 63 fall into the next L column / padding: finite garbage that is never used
                         const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
-                        N1[2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), N1[2 * w4]);
-                        N1[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), N1[2 * w4 + 1]);
+                        A1b[2 + 2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A1b[2 + 2 * w4]);
+                        A1b[3 + 2 * w4] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A1b[3 + 2 * w4]);
                     }
                 }
+                {
+                    const float2 qq = make_float2(qm[3], qm[3]);
+                    const float *col_c = Lc + 3 * GLD + j0 + 4;
 #pragma unroll
-                for (int w = 0; w < 16; ++w) A1b[w] = N1[w];
+                    for (int w4 = 0; w4 < 7; ++w4) {
+                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
+                        A1b[2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A1b[2 + 2 * w4]);
+                        A1b[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A1b[3 + 2 * w4]);
+                    }
+                }
             }
             __syncwarp();
             // ---------------- back substitution L^T x = z (column sweep): b0 / b1 hold z and turn into x
@@ -567,6 +530,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             if (lane == 0) mbar_arrive(bar_g_empty(g));           // L storage no longer needed
             T[row * D + lane] = x0;
             T[row * D + lane + 32] = x1;
+            __half h0, l0, h1, l1;
+            split_half(x0, h0, l0);
+            split_half(x1, h1, l1);
+            T_hi[row * D + lane] = h0; T_hi[row * D + lane + 32] = h1;
+            T_lo[row * D + lane] = l0; T_lo[row * D + lane + 32] = l1;
             if (bad && lane == 0) atomicAdd(info, 1);
         }
     }
@@ -577,32 +545,110 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
     }
 }
 
-}  // namespace tc
-
-int als_tc_supported(const fms_ctx *ctx, int rank) {
-    return rank == tc::D && ctx->smem_optin >= (size_t)tc::Smem::total + 1024;
+// fp32 factor rows -> gather planes (after init, after an all-gather, after the generic kernel wrote a side)
+__global__ void k_split_planes(const float *__restrict__ f, int64_t n, __half *__restrict__ hi, __half *__restrict__ lo) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    __half h, l;
+    split_half(f[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
 }
 
-int als_tc_refresh_planes(fms_ctx *, int) { return FMS_OK; }
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+int als_tc_supported(const fms_ctx *ctx, int rank) {
+    return rank == tc::D && ctx->smem_optin >= (size_t)tc::Smem::total + 1024 && get_encode_fn() != nullptr;
+}
+
+// planes of side s: [hi: rows x 64 halves][lo: rows x 64 halves], rows = padded rows + 8 (row `padded` stays zero)
+static int64_t plane_rows(const AlsState &A, int s) { return A.shard_rows[s] * A.shard_count + 8; }
+
+static int ensure_planes(fms_ctx *ctx, int s) {
+    AlsState &A = ctx->als;
+    const size_t need = (size_t)plane_rows(A, s) * tc::D * 2;
+    if (A.plane[s].n < need || !A.plane[s].p || A.plane_rows[s] != plane_rows(A, s)) {
+        FMS_CUDA(ctx, A.plane[s].alloc(need));
+        FMS_CUDA(ctx, cudaMemsetAsync(A.plane[s].p, 0, A.plane[s].n * sizeof(uint16_t), ctx->stream));
+        A.plane_rows[s] = plane_rows(A, s);
+        A.plane_valid[s] = false;
+    }
+    return FMS_OK;
+}
+
+int als_tc_refresh_planes(fms_ctx *ctx, int s) {
+    AlsState &A = ctx->als;
+    FMS_TRY(ensure_planes(ctx, s));
+    const int64_t n = (A.shard_rows[s] * A.shard_count) * tc::D;
+    if (n > 0) {
+        __half *hi = reinterpret_cast<__half *>(A.plane[s].p);
+        tc::k_split_planes<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(A.fac[s].p, n, hi, hi + (int64_t)plane_rows(A, s) * tc::D);
+        FMS_LAUNCH_CHECK(ctx);
+    }
+    A.plane_valid[s] = true;
+    return FMS_OK;
+}
+
+static int make_map(fms_ctx *ctx, CUtensorMap *m, void *base, int64_t rows) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)tc::D, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)tc::D * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::D, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, FMS_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+    return FMS_OK;
+}
 
 static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t re, float *dump) {
     AlsState &A = ctx->als;
     if (re <= rb) return FMS_OK;
+    const int partner = 1 - which;
+    FMS_TRY(ensure_planes(ctx, which));
+    FMS_TRY(ensure_planes(ctx, partner));
+    if (!A.plane_valid[partner]) FMS_TRY(als_tc_refresh_planes(ctx, partner));
+    const int64_t prow = plane_rows(A, partner), trow = plane_rows(A, which);
+    __half *p_hi = reinterpret_cast<__half *>(A.plane[partner].p), *t_hi = reinterpret_cast<__half *>(A.plane[which].p);
+    CUtensorMap m_hi, m_lo;
+    FMS_TRY(make_map(ctx, &m_hi, p_hi, prow));
+    FMS_TRY(make_map(ctx, &m_lo, p_hi + prow * tc::D, prow));
+    const int zero_row = (int)(A.shard_rows[partner] * A.shard_count);
     const size_t smem = (size_t)tc::Smem::total + 1024;
     const int64_t rows = re - rb;
     const unsigned grid = (unsigned)(rows < ctx->sm_count ? rows : ctx->sm_count);
     if (dump) {
         FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::k_als_rows_tc64<true><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(A.ptr[which].p, A.col[which].p, A.val[which].p,
-                                                                                 A.fac[1 - which].p, A.fac[which].p, lambda, rb, re,
-                                                                                 A.info.p, dump);
+        tc::k_als_rows_tc64<true><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_hi, m_lo, A.ptr[which].p, A.col[which].p, A.val[which].p,
+                                                                                 A.fac[which].p, t_hi, t_hi + trow * tc::D, zero_row, lambda,
+                                                                                 rb, re, A.info.p, dump);
     } else {
         FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::k_als_rows_tc64<false><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(A.ptr[which].p, A.col[which].p, A.val[which].p,
-                                                                                  A.fac[1 - which].p, A.fac[which].p, lambda, rb, re,
-                                                                                  A.info.p, nullptr);
+        tc::k_als_rows_tc64<false><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_hi, m_lo, A.ptr[which].p, A.col[which].p, A.val[which].p,
+                                                                                  A.fac[which].p, t_hi, t_hi + trow * tc::D, zero_row, lambda,
+                                                                                  rb, re, A.info.p, nullptr);
     }
     FMS_LAUNCH_CHECK(ctx);
+    // the kernel wrote the planes of its own rows; with one shard that is the whole side
+    A.plane_valid[which] = (A.shard_count == 1);
     return FMS_OK;
 }
 
@@ -610,7 +656,7 @@ int als_launch_half_step_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, i
     return launch_tc(ctx, which, lambda, rb, re, nullptr);
 }
 
-// test hook: Gramian + rhs of rows [rb, re) exactly as the solver warps receive them (row-major 64x64 + 64 floats each)
+// test hook: system matrix + rhs of rows [rb, re) exactly as the solver warps receive them (row-major 64x64 + 64 floats each)
 int als_tc_dump(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t re, float *d_dump) {
     return launch_tc(ctx, which, lambda, rb, re, d_dump);
 }

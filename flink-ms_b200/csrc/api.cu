@@ -141,10 +141,10 @@ FMS_API int fms_als_half_step(fms_ctx *ctx, int which, double lambda) {
     bool tc = false;
     if (A.kernel != FMS_ALS_KERNEL_GENERIC) tc = als_tc_supported(ctx, A.rank) != 0;
     if (A.kernel == FMS_ALS_KERNEL_TC && !tc) return fail(ctx, FMS_ERR_UNSUPPORTED, "tensor-core ALS kernel does not cover rank %d", A.rank);
+    A.fac64_valid = false;
+    A.plane_valid[which] = false;                      // the tensor-core kernel re-validates the planes it writes itself
     if (tc) FMS_TRY(als_launch_half_step_tc(ctx, which, (float)lambda, rb, re));
     else FMS_TRY(als_launch_half_step_generic(ctx, which, (float)lambda, rb, re));
-    A.fac64_valid = false;
-    A.plane_valid[which] = false;
     A.last_bad = -1;
     return FMS_OK;
 }

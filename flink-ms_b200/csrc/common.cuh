@@ -63,6 +63,7 @@ struct AlsState {
     // tensor-core path: split-precision gather planes (hi | lo fp16) per side, refreshed after each update
     DevBuf<uint16_t> plane[2];
     bool plane_valid[2] = {false, false};
+    int64_t plane_rows[2] = {0, 0};
     DevBuf<int32_t> order[2];                // row schedule (rows sorted by length, longest first)
 };
 
