@@ -26,6 +26,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 
 namespace fms {
@@ -37,11 +39,11 @@ constexpr int TILE_BYTES = KROWS * 128;           // one 64-wide operand chunk o
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // hi | lo | R | R'
 constexpr int NSTG = 8;                           // ring depth (64 KB, 32 KB of gathers in flight)
 constexpr int NACC = 2;                           // TMEM accumulator slots of 256 columns
-constexpr int N_EPI = 4, N_SOLVE = 8;
+constexpr int N_EPI = 4, N_SOLVE = 7, N_PROD = 4;
 constexpr int NGB = N_SOLVE;                      // one hand-off / L buffer per solver warp
 constexpr int GLD = 68;                           // row pitch of a hand-off buffer (floats)
-constexpr int W_EPI0 = 0, W_SOLVE0 = 4, W_MMA = 12, W_PROD = 13;
-constexpr int NWARPS = 14;
+constexpr int W_EPI0 = 0, W_SOLVE0 = 4, W_MMA = 11, W_PROD0 = 12;
+constexpr int NWARPS = 16;
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
 struct Smem {   // byte offsets from the 1024-aligned base
@@ -84,11 +86,19 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// TMA gather4: four rows (row indices r0..r3, 64 halves each) of a 2-D fp16 tensor -> 512 contiguous swizzled bytes
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *map, uint32_t bar, int r0, int r1, int r2, int r3) {
+// TMA gather4: four rows (row indices r0..r3, 64 halves each) of a 2-D fp16 tensor -> 512 contiguous swizzled bytes.
+// Issues the hi-plane and lo-plane gathers of one row quartet from ONE elected lane (the operands must be valid in
+// every lane: they come from warp shuffles), predicated instead of branched so the compiler emits no lane loop.
+__device__ __forceinline__ void tma_gather4_pair(uint32_t dst_hi, uint32_t dst_lo, const CUtensorMap *map_hi, const CUtensorMap *map_lo,
+                                                 uint32_t bar, int r0, int r1, int r2, int r3) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        "{\n"
+        ".reg .pred pe;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%2, {%5, %6, %7, %8, %9}], [%4];\n"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%1], [%3, {%5, %6, %7, %8, %9}], [%4];\n"
+        "}\n" ::"r"(dst_hi),
+        "r"(dst_lo), "l"(map_hi), "l"(map_lo), "r"(bar), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
         : "memory");
 }
 
@@ -207,9 +217,9 @@ __device__ __forceinline__ void panel_row(const Panel &p, float a0, float a1, fl
 template <bool DUMP>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
     const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const int64_t *__restrict__ ptr,
-    const int32_t *__restrict__ col, const float *__restrict__ val, float *__restrict__ T, __half *__restrict__ T_hi,
-    __half *__restrict__ T_lo, int zero_row, float lambda, int64_t row_begin, int64_t row_end, int *__restrict__ info,
-    float *__restrict__ dump) {
+    const int32_t *__restrict__ stage_ptr, const int32_t *__restrict__ colp, const float *__restrict__ valp,
+    const int32_t *__restrict__ cta_rows, float *__restrict__ T, __half *__restrict__ T_hi, __half *__restrict__ T_lo, float lambda,
+    int64_t row_begin, int *__restrict__ info, float *__restrict__ dump) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
     const uint32_t sm_base = smem_u32(sm);
@@ -241,38 +251,32 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t first = row_begin + blockIdx.x;
-    const int64_t stride = gridDim.x;
+    // this CTA owns the contiguous rows [first, last) == the stages [stage_ptr[first], stage_ptr[last])
+    const int64_t first = cta_rows[blockIdx.x], last = cta_rows[blockIdx.x + 1];
 
-    if (warp == W_PROD) {
-        // ================================================================== producer: CSR slice -> TMA gather4 + rating chunks
-        int64_t row = first, s0 = 0, e0 = 0;
-        uint32_t base = 0, nst = 0;                                // stage counters of the current row
-        auto load_row = [&]() { s0 = ptr[row]; e0 = ptr[row + 1]; nst = (uint32_t)((e0 - s0 + KROWS - 1) / KROWS); };
-        if (row < row_end) load_row();
-        // index / rating registers of the stage being issued and the two after it (lanes 0..15 hold one rating each)
-        int idx0 = zero_row, idx1 = zero_row, idx2 = zero_row;
-        float rt0 = 0.f, rt1 = 0.f, rt2 = 0.f;
-        bool ok0 = false, ok1 = false, ok2 = false;
-        auto fetch = [&](uint32_t c, int &idx, float &rt) -> bool {   // positions (row, base, ...) on stage c, loads its slice
-            while (row < row_end && c >= base + nst) {
-                base += nst;
-                row += stride;
-                if (row < row_end) load_row();
-            }
-            if (row >= row_end) { idx = zero_row; rt = 0.f; return false; }
-            const int64_t k = s0 + (int64_t)(c - base) * KROWS + (lane & 15);
-            const bool in = k < e0;
-            idx = in ? col[k] : zero_row;
-            rt = in ? val[k] : 0.f;
-            return true;
-        };
-        ok0 = fetch(0, idx0, rt0);
-        ok1 = ok0 ? fetch(1, idx1, rt1) : false;
-        ok2 = ok1 ? fetch(2, idx2, rt2) : false;
-        for (uint32_t c = 0; ok0; ++c) {
+    if (warp >= W_PROD0) {
+        // ================================================================== producers: stage stream -> TMA gather4 + rating chunks
+        // The ratings of a side are pre-laid as 16-entry stages (colp / valp, rows padded with the planes' zero row),
+        // so a producer warp just streams: stage s of this CTA lives at [16 s, 16 s + 16).
+        const uint32_t pw = (uint32_t)(warp - W_PROD0);           // this warp owns local stages pw, pw + N_PROD, ...
+        const int64_t s_lo = stage_ptr[first], s_hi = stage_ptr[last];
+        const uint32_t n_local = (uint32_t)(s_hi - s_lo);
+        const int32_t *cp = colp + s_lo * KROWS + (lane & 15);
+        const float *vp = valp + s_lo * KROWS + (lane & 15);
+        int idx0 = 0, idx1 = 0;
+        float rt0 = 0.f, rt1 = 0.f;
+        if (pw < n_local) { idx0 = cp[(int64_t)pw * KROWS]; rt0 = vp[(int64_t)pw * KROWS]; }
+        if (pw + N_PROD < n_local) { idx1 = cp[(int64_t)(pw + N_PROD) * KROWS]; rt1 = vp[(int64_t)(pw + N_PROD) * KROWS]; }
+        for (uint32_t c = pw; c < n_local; c += N_PROD) {
+            int idx2 = 0;
+            float rt2 = 0.f;
+            if (c + 2 * N_PROD < n_local) { idx2 = cp[(int64_t)(c + 2 * N_PROD) * KROWS]; rt2 = vp[(int64_t)(c + 2 * N_PROD) * KROWS]; }
             const int slot = c % NSTG;
             const uint32_t stage = sm_base + Smem::ring + slot * STAGE_BYTES;
+            // every lane gets the 16 row indices of the stage (lanes 0..15 hold one each)
+            int r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __shfl_sync(0xffffffffu, idx0, i);
             mbar_wait(bar_empty(slot), ((c / NSTG) & 1) ^ 1);
             // ratings: R row r = (r_hi, r_lo * 2^11, 0...), R' row r = (0, r_hi, 0...); 16-byte chunk 0 sits at chunk (r & 7)
             if (lane < 16) {
@@ -288,26 +292,19 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             __syncwarp();
             if (lane == 0) mbar_expect_tx(bar_full(slot), 2 * TILE_BYTES);
             __syncwarp();
-            // lane t (0..3) gathers rows 4t..4t+3 of both planes
-            const int g = (lane & 3) * 4;
-            const int r0 = __shfl_sync(0xffffffffu, idx0, g), r1 = __shfl_sync(0xffffffffu, idx0, g + 1);
-            const int r2 = __shfl_sync(0xffffffffu, idx0, g + 2), r3 = __shfl_sync(0xffffffffu, idx0, g + 3);
-            if (lane < 4) {
-                tma_gather4(stage + lane * 512, &map_hi, bar_full(slot), r0, r1, r2, r3);
-                tma_gather4(stage + TILE_BYTES + lane * 512, &map_lo, bar_full(slot), r0, r1, r2, r3);
-            }
-            // rotate the prefetch registers, fetch the slice three stages ahead
-            idx0 = idx1; rt0 = rt1; ok0 = ok1;
-            idx1 = idx2; rt1 = rt2; ok1 = ok2;
-            ok2 = ok1 ? fetch(c + 3, idx2, rt2) : false;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                tma_gather4_pair(stage + t * 512, stage + TILE_BYTES + t * 512, &map_hi, &map_lo, bar_full(slot), r[4 * t], r[4 * t + 1],
+                                 r[4 * t + 2], r[4 * t + 3]);
+            idx0 = idx1; rt0 = rt1;
+            idx1 = idx2; rt1 = rt2;
         }
     } else if (warp == W_MMA) {
         // ================================================================== MMA issuer
         uint32_t stage_ctr = 0, job = 0;
         const uint32_t id192 = make_idesc(192), id128 = make_idesc(128);
-        for (int64_t row = first; row < row_end; row += stride, ++job) {
-            const int64_t s0 = ptr[row], e0 = ptr[row + 1];
-            const int nst = (int)((e0 - s0 + KROWS - 1) / KROWS);
+        for (int64_t row = first; row < last; ++row, ++job) {
+            const int nst = stage_ptr[row + 1] - stage_ptr[row];
             const int acc = job % NACC;
             mbar_wait(bar_acc_empty(acc), ((job / NACC) & 1) ^ 1);
             tc_fence_after();
@@ -326,7 +323,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
         // ================================================================== epilogue: TMEM -> registers -> hand-off buffer
         const int q = warp - W_EPI0;                              // TMEM lane quadrant == warp index % 4
         uint32_t job = 0;
-        for (int64_t row = first; row < row_end; row += stride, ++job) {
+        for (int64_t row = first; row < last; ++row, ++job) {
             const int acc = job % NACC, g = job % NGB;
             const float reg = lambda * (float)(ptr[row + 1] - ptr[row]);
             mbar_wait(bar_acc_full(acc), (job / NACC) & 1);
@@ -371,7 +368,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
         float *G = reinterpret_cast<float *>(sm + Smem::gbuf + g * D * GLD * 4);
         const float *bi = reinterpret_cast<const float *>(sm + Smem::bsol + g * D * 4);
         uint32_t job = 0, use = 0;
-        for (int64_t row = first; row < row_end; row += stride, ++job) {
+        for (int64_t row = first; row < last; ++row, ++job) {
             if ((int)(job % N_SOLVE) != sv) continue;
             mbar_wait(bar_g_full(g), use & 1);
             ++use;
@@ -396,72 +393,62 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             bool bad = false;
 
             // ---------------- panels over columns 0..31 (pivot rows live in A0 / b0 of lanes j0..j0+3)
+            // Two passes over a 32-column register window; inside a pass the four panels sit at static window
+            // positions (no register rotation), between the passes the window moves down by 16 columns.
 #pragma unroll 1
-            for (int j0 = 0; j0 < 32; j0 += 4) {
-                const float d00 = __shfl_sync(0xffffffffu, A0[0].x, j0);
-                const float d10 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 1), d11 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 1);
-                const float d20 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 2), d21 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 2);
-                const float d22 = __shfl_sync(0xffffffffu, A0[1].x, j0 + 2);
-                const float d30 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 3), d31 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 3);
-                const float d32 = __shfl_sync(0xffffffffu, A0[1].x, j0 + 3), d33 = __shfl_sync(0xffffffffu, A0[1].y, j0 + 3);
-                const float zb0 = __shfl_sync(0xffffffffu, b0, j0), zb1 = __shfl_sync(0xffffffffu, b0, j0 + 1);
-                const float zb2 = __shfl_sync(0xffffffffu, b0, j0 + 2), zb3 = __shfl_sync(0xffffffffu, b0, j0 + 3);
-                const Panel P = panel_factor(d00, d10, d11, d20, d21, d22, d30, d31, d32, d33, zb0, zb1, zb2, zb3);
-                bad |= P.bad;
-                float p0, p1, p2, p3, q0, q1, q2, q3;
-                panel_row(P, A0[0].x, A0[0].y, A0[1].x, A0[1].y, p0, p1, p2, p3);
-                panel_row(P, A1a[0].x, A1a[0].y, A1a[1].x, A1a[1].y, q0, q1, q2, q3);
-                // rhs: rows below the panel get b_i -= sum_c L[i][c] z_c; pivot rows keep z; finished rows keep theirs
-                const float nb0 = fmaf(-p3, P.z3, fmaf(-p2, P.z2, fmaf(-p1, P.z1, fmaf(-p0, P.z0, b0))));
-                b1 = fmaf(-q3, P.z3, fmaf(-q2, P.z2, fmaf(-q1, P.z1, fmaf(-q0, P.z0, b1))));
-                const int rel = lane - j0;
-                b0 = rel == 0 ? P.z0 : rel == 1 ? P.z1 : rel == 2 ? P.z2 : rel == 3 ? P.z3 : rel > 3 ? nb0 : b0;
-                // publish the four L columns (column-major) and 1 / L_jj
-                float *Lc = Ls + j0 * GLD;
-                Lc[lane] = p0; Lc[GLD + lane] = p1; Lc[2 * GLD + lane] = p2; Lc[3 * GLD + lane] = p3;
-                Lc[lane + 32] = q0; Lc[GLD + lane + 32] = q1; Lc[2 * GLD + lane + 32] = q2; Lc[3 * GLD + lane + 32] = q3;
-                if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(P.i0, P.i1, P.i2, P.i3);
-                __syncwarp();
-                // trailing update.  Window positions 2..15 (columns j0+4 .. j0+31) are updated in place for the first
-                // three panel columns; the fourth update writes two positions down, which rotates the window for free.
-                const float pm[4] = {-p0, -p1, -p2, -p3}, qm[4] = {-q0, -q1, -q2, -q3};
+            for (int jw = 0; jw < 32; jw += 16) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float2 pp = make_float2(pm[c], pm[c]), qq = make_float2(qm[c], qm[c]);
-                    const float *col_c = Lc + c * GLD + j0 + 4;                       // L[j0+4 ..][j0+c]
+                for (int P = 0; P < 8; P += 2) {                   // window position of the panel, in float2 units
+                    const int j0 = jw + 2 * P;
+                    const float d00 = __shfl_sync(0xffffffffu, A0[P].x, j0);
+                    const float d10 = __shfl_sync(0xffffffffu, A0[P].x, j0 + 1), d11 = __shfl_sync(0xffffffffu, A0[P].y, j0 + 1);
+                    const float d20 = __shfl_sync(0xffffffffu, A0[P].x, j0 + 2), d21 = __shfl_sync(0xffffffffu, A0[P].y, j0 + 2);
+                    const float d22 = __shfl_sync(0xffffffffu, A0[P + 1].x, j0 + 2);
+                    const float d30 = __shfl_sync(0xffffffffu, A0[P].x, j0 + 3), d31 = __shfl_sync(0xffffffffu, A0[P].y, j0 + 3);
+                    const float d32 = __shfl_sync(0xffffffffu, A0[P + 1].x, j0 + 3), d33 = __shfl_sync(0xffffffffu, A0[P + 1].y, j0 + 3);
+                    const float zb0 = __shfl_sync(0xffffffffu, b0, j0), zb1 = __shfl_sync(0xffffffffu, b0, j0 + 1);
+                    const float zb2 = __shfl_sync(0xffffffffu, b0, j0 + 2), zb3 = __shfl_sync(0xffffffffu, b0, j0 + 3);
+                    const Panel PF = panel_factor(d00, d10, d11, d20, d21, d22, d30, d31, d32, d33, zb0, zb1, zb2, zb3);
+                    bad |= PF.bad;
+                    float p0, p1, p2, p3, q0, q1, q2, q3;
+                    panel_row(PF, A0[P].x, A0[P].y, A0[P + 1].x, A0[P + 1].y, p0, p1, p2, p3);
+                    panel_row(PF, A1a[P].x, A1a[P].y, A1a[P + 1].x, A1a[P + 1].y, q0, q1, q2, q3);
+                    // rhs: rows below the panel get b_i -= sum_c L[i][c] z_c; pivot rows keep z; finished rows keep theirs
+                    const float nb0 = fmaf(-p3, PF.z3, fmaf(-p2, PF.z2, fmaf(-p1, PF.z1, fmaf(-p0, PF.z0, b0))));
+                    b1 = fmaf(-q3, PF.z3, fmaf(-q2, PF.z2, fmaf(-q1, PF.z1, fmaf(-q0, PF.z0, b1))));
+                    const int rel = lane - j0;
+                    b0 = rel == 0 ? PF.z0 : rel == 1 ? PF.z1 : rel == 2 ? PF.z2 : rel == 3 ? PF.z3 : rel > 3 ? nb0 : b0;
+                    // publish the four L columns (column-major) and 1 / L_jj
+                    float *Lc = Ls + j0 * GLD;
+                    Lc[lane] = p0; Lc[GLD + lane] = p1; Lc[2 * GLD + lane] = p2; Lc[3 * GLD + lane] = p3;
+                    Lc[lane + 32] = q0; Lc[GLD + lane + 32] = q1; Lc[2 * GLD + lane + 32] = q2; Lc[3 * GLD + lane + 32] = q3;
+                    if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(PF.i0, PF.i1, PF.i2, PF.i3);
+                    __syncwarp();
+                    // trailing update of window positions P+2 .. 15 (columns j0+4 .. jw+31) and of columns 32..63
+                    const float pm[4] = {-p0, -p1, -p2, -p3}, qm[4] = {-q0, -q1, -q2, -q3};
 #pragma unroll
-                    for (int w4 = 0; w4 < 7; ++w4) {
-                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
-                        const float2 la = make_float2(lv.x, lv.y), lb = make_float2(lv.z, lv.w);
-                        A0[2 + 2 * w4] = __ffma2_rn(pp, la, A0[2 + 2 * w4]); A0[3 + 2 * w4] = __ffma2_rn(pp, lb, A0[3 + 2 * w4]);
-                        A1a[2 + 2 * w4] = __ffma2_rn(qq, la, A1a[2 + 2 * w4]); A1a[3 + 2 * w4] = __ffma2_rn(qq, lb, A1a[3 + 2 * w4]);
-                    }
-                    const float *col_s = Lc + c * GLD + 32;                           // L[32 ..][j0+c]
+                    for (int c = 0; c < 4; ++c) {
+                        const float2 pp = make_float2(pm[c], pm[c]), qq = make_float2(qm[c], qm[c]);
+                        const float *col_w = Lc + c * GLD + jw;                          // L[jw ..][j0+c]
 #pragma unroll
-                    for (int w4 = 0; w4 < 8; ++w4) {
-                        const float4 lv = *reinterpret_cast<const float4 *>(col_s + 4 * w4);
-                        A1b[2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A1b[2 * w4]);
-                        A1b[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A1b[2 * w4 + 1]);
-                    }
-                }
-                {
-                    const float2 pp = make_float2(pm[3], pm[3]), qq = make_float2(qm[3], qm[3]);
-                    const float *col_c = Lc + 3 * GLD + j0 + 4;
+                        for (int w = P + 2; w < 16; w += 2) {
+                            const float4 lv = *reinterpret_cast<const float4 *>(col_w + 2 * w);
+                            const float2 la = make_float2(lv.x, lv.y), lb = make_float2(lv.z, lv.w);
+                            A0[w] = __ffma2_rn(pp, la, A0[w]); A0[w + 1] = __ffma2_rn(pp, lb, A0[w + 1]);
+                            A1a[w] = __ffma2_rn(qq, la, A1a[w]); A1a[w + 1] = __ffma2_rn(qq, lb, A1a[w + 1]);
+                        }
+                        const float *col_s = Lc + c * GLD + 32;                          // L[32 ..][j0+c]
 #pragma unroll
-                    for (int w4 = 0; w4 < 7; ++w4) {
-                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
-                        const float2 la = make_float2(lv.x, lv.y), lb = make_float2(lv.z, lv.w);
-                        A0[2 * w4] = __ffma2_rn(pp, la, A0[2 + 2 * w4]); A0[2 * w4 + 1] = __ffma2_rn(pp, lb, A0[3 + 2 * w4]);
-                        A1a[2 * w4] = __ffma2_rn(qq, la, A1a[2 + 2 * w4]); A1a[2 * w4 + 1] = __ffma2_rn(qq, lb, A1a[3 + 2 * w4]);
-                    }
-                    const float *col_s = Lc + 3 * GLD + 32;
-#pragma unroll
-                    for (int w4 = 0; w4 < 8; ++w4) {
-                        const float4 lv = *reinterpret_cast<const float4 *>(col_s + 4 * w4);
-                        A1b[2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A1b[2 * w4]);
-                        A1b[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A1b[2 * w4 + 1]);
+                        for (int w4 = 0; w4 < 8; ++w4) {
+                            const float4 lv = *reinterpret_cast<const float4 *>(col_s + 4 * w4);
+                            A1b[2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A1b[2 * w4]);
+                            A1b[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A1b[2 * w4 + 1]);
+                        }
                     }
                 }
+                // move the window down by 16 columns (the vacated upper half only ever holds unused entries)
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { A0[w] = A0[w + 8]; A1a[w] = A1a[w + 8]; }
             }
             // ---------------- panels over columns 32..63 (pivot rows live in A1b / b1 of lanes j0-32 .. +3)
 #pragma unroll 1
@@ -511,20 +498,35 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                 }
             }
             __syncwarp();
-            // ---------------- back substitution L^T x = z (column sweep): b0 / b1 hold z and turn into x
+            // ---------------- back substitution L^T x = z, four columns at a time (column sweep): b0 / b1 hold z
             float x0 = 0.f, x1 = 0.f;
 #pragma unroll 1
-            for (int j = D - 1; j >= 32; --j) {
-                const float xj = __shfl_sync(0xffffffffu, b1, j - 32) * invd[j];
-                if (lane == j - 32) x1 = xj;
-                b0 = fmaf(-Ls[lane * GLD + j], xj, b0);                               // L[j][lane], lane < 32 <= j
-                if (lane + 32 < j) b1 = fmaf(-Ls[(lane + 32) * GLD + j], xj, b1);
-            }
-#pragma unroll 1
-            for (int j = 31; j >= 0; --j) {
-                const float xj = __shfl_sync(0xffffffffu, b0, j) * invd[j];
-                if (lane == j) x0 = xj;
-                if (lane < j) b0 = fmaf(-Ls[lane * GLD + j], xj, b0);
+            for (int j0 = D - 4; j0 >= 0; j0 -= 4) {
+                const bool hiside = j0 >= 32;                      // pivot rows live in b1 (lanes j0-32..) or b0 (lanes j0..)
+                const int src = hiside ? j0 - 32 : j0;
+                const float zsrc = hiside ? b1 : b0;
+                const float z0 = __shfl_sync(0xffffffffu, zsrc, src), z1 = __shfl_sync(0xffffffffu, zsrc, src + 1);
+                const float z2 = __shfl_sync(0xffffffffu, zsrc, src + 2), z3 = __shfl_sync(0xffffffffu, zsrc, src + 3);
+                const float4 c0 = *reinterpret_cast<const float4 *>(Ls + (j0 + 0) * GLD + j0);   // L[j0..j0+3][j0]
+                const float4 c1 = *reinterpret_cast<const float4 *>(Ls + (j0 + 1) * GLD + j0);   // L[..][j0+1]
+                const float4 c2 = *reinterpret_cast<const float4 *>(Ls + (j0 + 2) * GLD + j0);
+                const float4 iv = *reinterpret_cast<const float4 *>(invd + j0);
+                const float v3 = z3 * iv.w;
+                const float v2 = fmaf(-c2.w, v3, z2) * iv.z;
+                const float v1 = fmaf(-c1.w, v3, fmaf(-c1.z, v2, z1)) * iv.y;
+                const float v0 = fmaf(-c0.w, v3, fmaf(-c0.z, v2, fmaf(-c0.y, v1, z0))) * iv.x;
+                const int rel = lane - src;
+                const float mine = rel == 0 ? v0 : rel == 1 ? v1 : rel == 2 ? v2 : v3;
+                if (rel >= 0 && rel < 4) { if (hiside) x1 = mine; else x0 = mine; }
+                // z_i -= sum_c L[j0+c][i] x_c for the rows above the panel
+                if (lane < j0) {
+                    const float4 lr = *reinterpret_cast<const float4 *>(Ls + lane * GLD + j0);   // L[j0..j0+3][lane]
+                    b0 = fmaf(-lr.w, v3, fmaf(-lr.z, v2, fmaf(-lr.y, v1, fmaf(-lr.x, v0, b0))));
+                }
+                if (lane + 32 < j0) {
+                    const float4 lr = *reinterpret_cast<const float4 *>(Ls + (lane + 32) * GLD + j0);
+                    b1 = fmaf(-lr.w, v3, fmaf(-lr.z, v2, fmaf(-lr.y, v1, fmaf(-lr.x, v0, b1))));
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_g_empty(g));           // L storage no longer needed
@@ -553,6 +555,42 @@ __global__ void k_split_planes(const float *__restrict__ f, int64_t n, __half *_
     split_half(f[i], h, l);
     hi[i] = h;
     lo[i] = l;
+}
+
+// ---- stage CSR build (one-off per load / shard geometry)
+__global__ void k_stage_counts(const int64_t *__restrict__ ptr, int64_t n_rows, int32_t *__restrict__ cnt) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r > n_rows) return;
+    cnt[r] = r < n_rows ? (int32_t)((ptr[r + 1] - ptr[r] + KROWS - 1) / KROWS) : 0;
+}
+__global__ void k_fill_stages(const int64_t *__restrict__ ptr, const int32_t *__restrict__ col, const float *__restrict__ val,
+                              const int32_t *__restrict__ stage_ptr, int64_t n_rows, int zero_row, int32_t *__restrict__ colp,
+                              float *__restrict__ valp) {
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const int64_t s = ptr[row], e = ptr[row + 1];
+    const int64_t base = (int64_t)stage_ptr[row] * KROWS;
+    const int64_t n_pad = (int64_t)(stage_ptr[row + 1] - stage_ptr[row]) * KROWS;
+    for (int64_t t = lane; t < n_pad; t += 32) {
+        const int64_t k = s + t;
+        colp[base + t] = k < e ? col[k] : zero_row;
+        valp[base + t] = k < e ? val[k] : 0.f;
+    }
+}
+// cta_rows[b] = first row of CTA b: rows [rb, re) split into `grid` contiguous ranges of (nearly) equal stage count
+__global__ void k_cta_partition(const int32_t *__restrict__ stage_ptr, int64_t rb, int64_t re, int grid, int32_t *__restrict__ cta_rows) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > grid) return;
+    if (b == grid) { cta_rows[b] = (int32_t)re; return; }
+    const int64_t s_lo = stage_ptr[rb], s_hi = stage_ptr[re];
+    const int64_t target = s_lo + ((s_hi - s_lo) * b) / grid;
+    int64_t lo = rb, hi = re;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (stage_ptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    cta_rows[b] = (int32_t)lo;
 }
 
 }  // namespace tc
@@ -619,6 +657,47 @@ static int make_map(fms_ctx *ctx, CUtensorMap *m, void *base, int64_t rows) {
     return FMS_OK;
 }
 
+static int ensure_stage_csr(fms_ctx *ctx, int which, int64_t rb, int64_t re, int zero_row, int grid) {
+    AlsState &A = ctx->als;
+    const int64_t n = which == 0 ? A.n_users : A.n_items;
+    cudaStream_t st = ctx->stream;
+    const bool refill = A.stage_zero_row[which] != zero_row || A.stage_rb[which] < 0;
+    if (refill) {
+        DevBuf<int32_t> cnt;
+        DevBuf<unsigned char> temp;
+        FMS_CUDA(ctx, cnt.alloc((size_t)n + 1));
+        FMS_CUDA(ctx, A.stage_ptr[which].alloc((size_t)n + 1));
+        tc::k_stage_counts<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(A.ptr[which].p, n, cnt.p);
+        FMS_LAUNCH_CHECK(ctx);
+        size_t tb = 0;
+        FMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, A.stage_ptr[which].p, n + 1, st));
+        FMS_CUDA(ctx, temp.alloc(tb));
+        FMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(temp.p, tb, cnt.p, A.stage_ptr[which].p, n + 1, st));
+        ctx->launches += 1;
+        int32_t total = 0;
+        FMS_CUDA(ctx, cudaMemcpyAsync(&total, A.stage_ptr[which].p + n, sizeof total, cudaMemcpyDeviceToHost, st));
+        FMS_CUDA(ctx, cudaStreamSynchronize(st));
+        A.total_stages[which] = total;
+        FMS_CUDA(ctx, A.colp[which].alloc((size_t)total * tc::KROWS));
+        FMS_CUDA(ctx, A.valp[which].alloc((size_t)total * tc::KROWS));
+        if (n > 0) {
+            tc::k_fill_stages<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(A.ptr[which].p, A.col[which].p, A.val[which].p,
+                                                                              A.stage_ptr[which].p, n, zero_row, A.colp[which].p,
+                                                                              A.valp[which].p);
+            FMS_LAUNCH_CHECK(ctx);
+        }
+        A.stage_zero_row[which] = zero_row;
+        A.stage_rb[which] = -2;                                    // force the partition below
+    }
+    if (A.stage_rb[which] != rb || A.stage_re[which] != re || A.stage_grid[which] != grid) {
+        FMS_CUDA(ctx, A.cta_rows[which].alloc((size_t)grid + 1));
+        tc::k_cta_partition<<<(grid + 1 + 127) / 128, 128, 0, st>>>(A.stage_ptr[which].p, rb, re, grid, A.cta_rows[which].p);
+        FMS_LAUNCH_CHECK(ctx);
+        A.stage_rb[which] = rb; A.stage_re[which] = re; A.stage_grid[which] = grid;
+    }
+    return FMS_OK;
+}
+
 static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t re, float *dump) {
     AlsState &A = ctx->als;
     if (re <= rb) return FMS_OK;
@@ -634,17 +713,20 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
     const int zero_row = (int)(A.shard_rows[partner] * A.shard_count);
     const size_t smem = (size_t)tc::Smem::total + 1024;
     const int64_t rows = re - rb;
-    const unsigned grid = (unsigned)(rows < ctx->sm_count ? rows : ctx->sm_count);
+    const int grid = (int)(rows < ctx->sm_count ? rows : ctx->sm_count);
+    FMS_TRY(ensure_stage_csr(ctx, which, rb, re, zero_row, grid));
     if (dump) {
         FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::k_als_rows_tc64<true><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_hi, m_lo, A.ptr[which].p, A.col[which].p, A.val[which].p,
-                                                                                 A.fac[which].p, t_hi, t_hi + trow * tc::D, zero_row, lambda,
-                                                                                 rb, re, A.info.p, dump);
+        tc::k_als_rows_tc64<true><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_hi, m_lo, A.ptr[which].p, A.stage_ptr[which].p,
+                                                                                 A.colp[which].p, A.valp[which].p, A.cta_rows[which].p,
+                                                                                 A.fac[which].p, t_hi, t_hi + trow * tc::D, lambda, rb,
+                                                                                 A.info.p, dump);
     } else {
         FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::k_als_rows_tc64<false><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_hi, m_lo, A.ptr[which].p, A.col[which].p, A.val[which].p,
-                                                                                  A.fac[which].p, t_hi, t_hi + trow * tc::D, zero_row, lambda,
-                                                                                  rb, re, A.info.p, nullptr);
+        tc::k_als_rows_tc64<false><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_hi, m_lo, A.ptr[which].p, A.stage_ptr[which].p,
+                                                                                  A.colp[which].p, A.valp[which].p, A.cta_rows[which].p,
+                                                                                  A.fac[which].p, t_hi, t_hi + trow * tc::D, lambda, rb,
+                                                                                  A.info.p, nullptr);
     }
     FMS_LAUNCH_CHECK(ctx);
     // the kernel wrote the planes of its own rows; with one shard that is the whole side

@@ -100,6 +100,8 @@ FMS_API int fms_als_load(fms_ctx *ctx, const int64_t *user, const int64_t *item,
     A.loaded = A.inited = false;
     A.model_external = false;
     FMS_TRY(als_build_csr(ctx, user, item, rating, nnz));
+    A.stage_rb[0] = A.stage_rb[1] = -1;                // stage layout of the tensor-core path is rebuilt lazily
+    A.stage_zero_row[0] = A.stage_zero_row[1] = -1;
     A.shard_index = shard_index;
     A.shard_count = shard_count;
     A.shard_rows[0] = (A.n_users + shard_count - 1) / shard_count;

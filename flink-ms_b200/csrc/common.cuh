@@ -64,7 +64,15 @@ struct AlsState {
     DevBuf<uint16_t> plane[2];
     bool plane_valid[2] = {false, false};
     int64_t plane_rows[2] = {0, 0};
-    DevBuf<int32_t> order[2];                // row schedule (rows sorted by length, longest first)
+    // tensor-core path: ratings re-laid in 16-rating stages per row (padded), see als_tc.cu
+    DevBuf<int32_t> stage_ptr[2];            // per row: first stage (exclusive scan of ceil(n_row / 16)), N + 1 entries
+    DevBuf<int32_t> colp[2];                 // 16 * total_stages partner indices (padding -> zero row of the planes)
+    DevBuf<float> valp[2];                   // 16 * total_stages ratings (padding -> 0)
+    DevBuf<int32_t> cta_rows[2];             // row range boundaries per CTA (balanced by stage count)
+    int64_t total_stages[2] = {0, 0};
+    int stage_grid[2] = {0, 0};
+    int64_t stage_rb[2] = {-1, -1}, stage_re[2] = {-1, -1};
+    int stage_zero_row[2] = {-1, -1};
 };
 
 // --------------------------------------------------------------------------------------------- SVM state
