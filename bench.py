@@ -160,7 +160,7 @@ def main():
     ap.add_argument("--rank", type=int, default=64)
     ap.add_argument("--svm-n", type=int, default=10_000_000)
     ap.add_argument("--svm-dim", type=int, default=1024)
-    ap.add_argument("--svm-blocks-per-gpu", type=int, default=1184)
+    ap.add_argument("--svm-blocks-per-gpu", type=int, default=3552)
     ap.add_argument("--svm-rounds", type=int, default=3)
     ap.add_argument("--skip-svm", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -189,6 +189,7 @@ def main():
     synth = importlib.import_module("flink-ms_b200.synth")
     N = fms._native
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")           # keep NCCL's version banner off stdout (one JSON line only)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

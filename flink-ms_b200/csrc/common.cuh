@@ -175,6 +175,18 @@ struct JRand {
             if ((int)((unsigned)u - (unsigned)r + (unsigned)m) >= 0) return r;
         }
     }
+    // Same stream as next_int_bound, with the `u % bound` done by Lemire's exact fast-modulo
+    // (magic = 2^64 / bound + 1, exact for 32-bit operands): bit-identical results, no integer division.
+    __host__ __device__ static unsigned long long magic_for(int bound) { return 0xFFFFFFFFFFFFFFFFULL / (unsigned long long)bound + 1ULL; }
+    __device__ int next_int_bound_fast(int bound, unsigned long long magic) {
+        int r = next(31);
+        const int m = bound - 1;
+        if ((bound & m) == 0) return (int)(((long long)bound * (long long)r) >> 31);
+        for (int u = r;; u = next(31)) {
+            r = (int)__umul64hi(magic * (unsigned long long)(unsigned)u, (unsigned long long)bound);
+            if ((int)((unsigned)u - (unsigned)r + (unsigned)m) >= 0) return r;
+        }
+    }
     __host__ __device__ double next_double() {
         long long hi = (long long)next(26);
         long long lo = (long long)next(27);

@@ -6,8 +6,9 @@
 //   * one warp owns one CoCoA block for the whole round; its private copy of w and its dw live in registers
 //     (lane l holds floats [128 v + 4 l, +4) for v < NV4), so a step touches HBM only for the row, y and alpha;
 //   * the sampled-row sequence does not depend on w, so rows are fetched STAGES steps ahead by the TMA engine
-//     (cp.async.bulk global -> shared, mbarrier complete_tx) into a per-warp ring; y / alpha / row ids are
-//     prefetched in registers one and two steps ahead;
+//     (cp.async.bulk global -> shared, mbarrier complete_tx) into a per-warp ring; the step's label and alpha are
+//     fetched with it (STAGES steps ahead, patched when an earlier in-flight step rewrites the same alpha) and
+//     the row ids are drawn three further steps ahead, so no scalar load sits on the critical path;
 //   * the only cross-lane traffic per step is one fused 2-value butterfly (x.w and x.x).
 // Algorithmic bytes per step: 4*dim (row) + 4 (y) + 8 (alpha read+write).  HBM-bound; no tensor cores.
 #include "common.cuh"
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_svm_sweep_warp(
     const float *__restrict__ X, const float *__restrict__ y, float *alpha, const int32_t *__restrict__ rows,
     const int64_t *__restrict__ blk_ptr, const int32_t *__restrict__ local_blocks, int n_local,
     unsigned long long *__restrict__ rng_state, const float *__restrict__ w0, float *__restrict__ dw_out,
-    long long local_iterations, float lambda_n) {
+    long long local_iterations, float lambda_n, float inv_lambda_n) {
     constexpr int D = 128 * NV4;
     constexpr uint32_t ROW_BYTES = D * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -85,26 +86,34 @@ __global__ void __launch_bounds__(WARPS * 32) k_svm_sweep_warp(
         }
         __syncwarp();
 
-        // ---- producer side: row ids STAGES (+1 in flight) steps ahead of the consumer
-        JRand rng_p, rng_c;
-        rng_p.s = rng_c.s = rng_state[blk];
+        // ---- one RNG stream, drawn RD steps ahead of the row fetches, which run STAGES steps ahead of the maths.
+        // Every per-step scalar (row id, y, alpha) is therefore in flight for >= 3 steps: nothing on the critical path
+        // waits for DRAM.  Draws are guarded by the step count so the saved RNG state is the state after exactly H draws.
+        JRand rng;
+        rng.s = rng_state[blk];
+        long long drawn = 0;
+        const unsigned long long magic = JRand::magic_for(nk);
+        auto draw = [&]() -> int {
+            if (drawn >= H) return 0;
+            ++drawn;
+            return rws[rng.next_int_bound_fast(nk, magic)];
+        };
+        int rq[STAGES];                                           // row id of the step that owns ring stage s
+        float yq[STAGES], aq[STAGES];                             // its label and (lane 0) its alpha
+#pragma unroll
         for (int s = 0; s < STAGES; ++s) {                        // prologue: steps 0 .. STAGES-1
+            rq[s] = 0; yq[s] = 0.f; aq[s] = 0.f;
             if (s < H) {
-                const int row = rws[rng_p.next_int_bound(nk)];
+                rq[s] = draw();
                 if (lane == 0) {
                     mbar_expect_tx(smem_u32(&bars[s]), ROW_BYTES);
-                    bulk_g2s(smem_u32(ring + s * D), X + (size_t)row * D, ROW_BYTES, smem_u32(&bars[s]), policy);
+                    bulk_g2s(smem_u32(ring + s * D), X + (size_t)rq[s] * D, ROW_BYTES, smem_u32(&bars[s]), policy);
                 }
+                yq[s] = y[rq[s]];
+                aq[s] = (lane == 0) ? alpha[rq[s]] : 0.f;
             }
         }
-        int row_pending = (STAGES < H) ? rws[rng_p.next_int_bound(nk)] : 0;      // row of step STAGES
-
-        // ---- consumer side scalar pipeline: (row, y, alpha) of step t, t+1; row of t+2
-        int row_cur = rws[rng_c.next_int_bound(nk)];
-        float y_cur = y[row_cur];
-        float a_cur = __shfl_sync(0xffffffffu, lane == 0 ? alpha[row_cur] : 0.f, 0);
-        int row_n1 = (1 < H) ? rws[rng_c.next_int_bound(nk)] : row_cur;
-        int row_n2 = (2 < H) ? rws[rng_c.next_int_bound(nk)] : row_cur;
+        int rp0 = draw(), rp1 = draw(), rp2 = draw();             // rows of steps STAGES, STAGES+1, STAGES+2
 
         for (long long base = 0; base < H; base += STAGES) {
             const uint32_t parity = (uint32_t)((base / STAGES) & 1);
@@ -112,60 +121,67 @@ __global__ void __launch_bounds__(WARPS * 32) k_svm_sweep_warp(
             for (int s = 0; s < STAGES; ++s) {
                 const long long t = base + s;
                 if (t >= H) break;
-                // prefetch the scalars of step t+1 (issued before this step's alpha store: see the fix-up below)
-                const float y_n1 = y[row_n1];
-                float a_n1 = (lane == 0) ? alpha[row_n1] : 0.f;
-                // wait for this step's row
                 const uint32_t bar = smem_u32(&bars[s]);
                 while (!mbar_try_wait(bar, parity)) {}
                 const float4 *xs = reinterpret_cast<const float4 *>(ring + s * D);
                 float4 x[NV4];
 #pragma unroll
                 for (int v = 0; v < NV4; ++v) x[v] = xs[v * 32 + lane];
-                float d0 = 0.f, d1 = 0.f, q0 = 0.f, q1 = 0.f;
+                float2 dd = make_float2(0.f, 0.f), qq = make_float2(0.f, 0.f);   // packed partials of x.w and x.x
 #pragma unroll
                 for (int v = 0; v < NV4; ++v) {
-                    d0 = fmaf(x[v].x, w[v].x, d0); d1 = fmaf(x[v].y, w[v].y, d1);
-                    d0 = fmaf(x[v].z, w[v].z, d0); d1 = fmaf(x[v].w, w[v].w, d1);
-                    q0 = fmaf(x[v].x, x[v].x, q0); q1 = fmaf(x[v].y, x[v].y, q1);
-                    q0 = fmaf(x[v].z, x[v].z, q0); q1 = fmaf(x[v].w, x[v].w, q1);
+                    const float2 xa = make_float2(x[v].x, x[v].y), xb = make_float2(x[v].z, x[v].w);
+                    dd = __ffma2_rn(xa, make_float2(w[v].x, w[v].y), dd); dd = __ffma2_rn(xb, make_float2(w[v].z, w[v].w), dd);
+                    qq = __ffma2_rn(xa, xa, qq); qq = __ffma2_rn(xb, xb, qq);
                 }
-                float dot = d0 + d1, q = q0 + q1;
+                float dot = dd.x + dd.y, q = qq.x + qq.y;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     dot += __shfl_xor_sync(0xffffffffu, dot, o);
                     q += __shfl_xor_sync(0xffffffffu, q, o);
                 }
+                const int row_cur = rq[s];
+                const float y_cur = yq[s];
+                const float a_cur = __shfl_sync(0xffffffffu, aq[s], 0);
                 // the row buffer is free again: refill it with the row of step t + STAGES
+                const bool more = t + STAGES < H;
+                const int row_new = rp0;
                 __syncwarp();
-                if (t + STAGES < H && lane == 0) {
+                if (more && lane == 0) {
                     mbar_expect_tx(bar, ROW_BYTES);
-                    bulk_g2s(smem_u32(ring + s * D), X + (size_t)row_pending * D, ROW_BYTES, bar, policy);
+                    bulk_g2s(smem_u32(ring + s * D), X + (size_t)row_new * D, ROW_BYTES, bar, policy);
                 }
-                if (t + STAGES + 1 < H) row_pending = rws[rng_p.next_int_bound(nk)];
                 // maximize()
                 const float g = (y_cur * dot - 1.f) * lambda_n;
                 float a_new = a_cur;
                 if (g != 0.f) {
-                    a_new = (q != 0.f) ? fminf(fmaxf(a_cur - g / q, 0.f), 1.f) : 1.f;
-                    const float c = y_cur * (a_new - a_cur) / lambda_n;
+                    a_new = (q != 0.f) ? fminf(fmaxf(a_cur - __fdividef(g, q), 0.f), 1.f) : 1.f;
+                    const float c = y_cur * (a_new - a_cur) * inv_lambda_n;
+                    const float2 cc = make_float2(c, c);
 #pragma unroll
                     for (int v = 0; v < NV4; ++v) {
-                        float t0 = c * x[v].x, t1 = c * x[v].y, t2 = c * x[v].z, t3 = c * x[v].w;
-                        w[v].x += t0; w[v].y += t1; w[v].z += t2; w[v].w += t3;
-                        dw[v].x += t0; dw[v].y += t1; dw[v].z += t2; dw[v].w += t3;
+                        const float2 xa = make_float2(x[v].x, x[v].y), xb = make_float2(x[v].z, x[v].w);
+                        const float2 wa = __ffma2_rn(cc, xa, make_float2(w[v].x, w[v].y)), wb = __ffma2_rn(cc, xb, make_float2(w[v].z, w[v].w));
+                        const float2 da = __ffma2_rn(cc, xa, make_float2(dw[v].x, dw[v].y)), db = __ffma2_rn(cc, xb, make_float2(dw[v].z, dw[v].w));
+                        w[v] = make_float4(wa.x, wa.y, wb.x, wb.y);
+                        dw[v] = make_float4(da.x, da.y, db.x, db.y);
                     }
                     if (lane == 0) alpha[row_cur] = a_new;
                 }
-                // rotate the scalar pipeline; alpha[row_n1] was read before the store above
-                a_n1 = __shfl_sync(0xffffffffu, a_n1, 0);
-                if (row_n1 == row_cur) a_n1 = a_new;
-                row_cur = row_n1; y_cur = y_n1; a_cur = a_n1;
-                row_n1 = row_n2;
-                if (t + 3 < H) row_n2 = rws[rng_c.next_int_bound(nk)];
+                // alpha values already prefetched for the in-flight steps were read before this store
+#pragma unroll
+                for (int s2 = 0; s2 < STAGES; ++s2)
+                    if (s2 != s && rq[s2] == row_cur) aq[s2] = a_new;
+                // scalars of step t + STAGES (loads issued after the store above: same-lane program order)
+                if (more) {
+                    rq[s] = row_new;
+                    yq[s] = y[row_new];
+                    aq[s] = (lane == 0) ? alpha[row_new] : 0.f;
+                }
+                rp0 = rp1; rp1 = rp2; rp2 = draw();
             }
         }
-        if (lane == 0) rng_state[blk] = rng_c.s;
+        if (lane == 0) rng_state[blk] = rng.s;
     }
 #pragma unroll
     for (int v = 0; v < NV4; ++v) dwo[v * 32 + lane] = dw[v];
@@ -181,7 +197,7 @@ int launch(fms_ctx *ctx, float *alpha_work, int64_t local_iterations) {
     const float lambda_n = (float)(S.lambda * (double)S.n);
     k_svm_sweep_warp<NV4><<<(n_local + WARPS - 1) / WARPS, WARPS * 32, smem, ctx->stream>>>(
         S.X, S.y.p, alpha_work, S.rows32.p, S.blk_ptr.p, S.d_local_blocks.p, n_local, (unsigned long long *)S.rng.p, S.w.p,
-        S.dw_blocks.p, (long long)local_iterations, lambda_n);
+        S.dw_blocks.p, (long long)local_iterations, lambda_n, (float)(1.0 / (S.lambda * (double)S.n)));
     FMS_LAUNCH_CHECK(ctx);
     return FMS_OK;
 }
