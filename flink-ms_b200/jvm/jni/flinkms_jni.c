@@ -1,0 +1,89 @@
+/*
+ * flinkms_jni.c -- thin JNI shim: de.tub.it4bi.gpu.Native -> the C-ABI of include/flinkms.h.
+ * Mechanical by design: unwrap direct ByteBuffers (GetDirectBufferAddress), call fms_*, turn a non-zero status
+ * into java.lang.RuntimeException(fms_last_error).  No pointer is retained past a call.
+ *
+ * NOT COMPILED HERE (the image has no JDK / jni.h).  Build where a JDK exists:
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../../include flinkms_jni.c \
+ *       -L.. -lflinkms_b200 -Wl,-rpath,'$ORIGIN' -o libflinkms_jni.so
+ */
+#include <jni.h>
+#include <stdint.h>
+
+#include "flinkms.h"
+
+static void *buf(JNIEnv *env, jobject b) { return b ? (*env)->GetDirectBufferAddress(env, b) : NULL; }
+
+static int check(JNIEnv *env, fms_ctx *ctx, int rc) {
+    if (rc == FMS_OK) return 0;
+    jclass ex = (*env)->FindClass(env, "java/lang/RuntimeException");
+    if (ex) (*env)->ThrowNew(env, ex, fms_last_error(ctx));
+    return rc;
+}
+
+JNIEXPORT jlong JNICALL Java_de_tub_it4bi_gpu_Native_create(JNIEnv *env, jclass cls, jint device) {
+    (void)cls;
+    fms_ctx *ctx = NULL;
+    int dev = (int)device;
+    if (check(env, NULL, fms_create(&ctx, &dev, 1))) return 0;
+    return (jlong)(intptr_t)ctx;
+}
+
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_destroy(JNIEnv *env, jclass cls, jlong ctx) {
+    (void)env; (void)cls;
+    fms_destroy((fms_ctx *)(intptr_t)ctx);
+}
+
+JNIEXPORT jlongArray JNICALL Java_de_tub_it4bi_gpu_Native_alsFit(JNIEnv *env, jclass cls, jlong c, jobject user, jobject item,
+                                                                 jobject rating, jlong nnz, jint rank, jint iterations,
+                                                                 jdouble lambda, jlong seed) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    int64_t n[2] = {0, 0};
+    if (check(env, ctx, fms_als_fit(ctx, buf(env, user), buf(env, item), buf(env, rating), nnz, rank, iterations, lambda, seed,
+                                    &n[0], &n[1]))) return NULL;
+    jlongArray out = (*env)->NewLongArray(env, 2);
+    jlong v[2] = {(jlong)n[0], (jlong)n[1]};
+    (*env)->SetLongArrayRegion(env, out, 0, 2, v);
+    return out;
+}
+
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_alsGetFactors(JNIEnv *env, jclass cls, jlong c, jint which, jobject ids,
+                                                                  jobject factors) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    check(env, ctx, fms_als_get_factors(ctx, which, buf(env, ids), buf(env, factors)));
+}
+
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_alsSetModel(JNIEnv *env, jclass cls, jlong c, jobject uids, jobject uf,
+                                                                jlong nu, jobject iids, jobject itf, jlong ni, jint rank) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    check(env, ctx, fms_als_set_model(ctx, buf(env, uids), buf(env, uf), nu, buf(env, iids), buf(env, itf), ni, rank));
+}
+
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_alsPredict(JNIEnv *env, jclass cls, jlong c, jobject u, jobject i, jlong n,
+                                                               jobject out, jobject found) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    check(env, ctx, fms_als_predict(ctx, buf(env, u), buf(env, i), n, buf(env, out), buf(env, found)));
+}
+
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_svmFit(JNIEnv *env, jclass cls, jlong c, jobject x, jint xDtype, jobject csrPtr,
+                                                           jobject csrIdx, jobject y, jlong n, jint dim, jobject blockId, jint blocks,
+                                                           jint iterations, jlong localIterations, jdouble regularization,
+                                                           jdouble stepsize, jlong seed, jint rngMode, jobject w) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    check(env, ctx, fms_svm_fit(ctx, buf(env, x), xDtype, buf(env, csrPtr), buf(env, csrIdx), buf(env, y), n, dim, buf(env, blockId),
+                                blocks, iterations, localIterations, regularization, stepsize, seed, rngMode, buf(env, w)));
+}
+
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_svmPredict(JNIEnv *env, jclass cls, jlong c, jobject x, jint xDtype,
+                                                               jobject csrPtr, jobject csrIdx, jlong n, jint dim, jobject w,
+                                                               jdouble threshold, jboolean decision, jobject out) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    check(env, ctx, fms_svm_predict(ctx, buf(env, x), xDtype, buf(env, csrPtr), buf(env, csrIdx), n, dim, buf(env, w), threshold,
+                                    decision ? 1 : 0, buf(env, out)));
+}

@@ -1,0 +1,59 @@
+package de.tub.it4bi.gpu;
+
+import java.nio.ByteBuffer;
+
+/**
+ * JNI binding of libflinkms_b200.so (C-ABI: include/flinkms.h).  One instance == one fms_ctx == one GPU; not
+ * thread-safe (create one per Flink task thread, like the reference's QueryClientHelper, SGD.java:137).
+ * All bulk arguments are DIRECT ByteBuffers in native byte order; the shim never retains their addresses.
+ * A non-zero fms_status is turned into a RuntimeException carrying fms_last_error().
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no JDK (SURVEY.md, "READ THIS FIRST" item 3).
+ */
+public final class Native implements AutoCloseable {
+    static { System.loadLibrary("flinkms_jni"); }   // flinkms_jni links libflinkms_b200.so
+
+    private long ctx;                                // fms_ctx*
+
+    public Native(int device) { ctx = create(device); }
+
+    @Override public void close() { if (ctx != 0) { destroy(ctx); ctx = 0; } }
+
+    // ---- ALS (replaces als.fit / factorsOption, ALSImpl.scala:52-57)
+    /** user/item: nnz int64, rating: nnz float64.  Returns {nUsers, nItems}. */
+    public long[] alsFit(ByteBuffer user, ByteBuffer item, ByteBuffer rating, long nnz, int rank, int iterations,
+                         double lambda, long seed) { return alsFit(ctx, user, item, rating, nnz, rank, iterations, lambda, seed); }
+    /** ids: n int64 (ascending), factors: n*rank float64 row-major. which: 0 = users, 1 = items. */
+    public void alsGetFactors(int which, ByteBuffer ids, ByteBuffer factors) { alsGetFactors(ctx, which, ids, factors); }
+    public void alsSetModel(ByteBuffer userIds, ByteBuffer userFactors, long nUsers, ByteBuffer itemIds, ByteBuffer itemFactors,
+                            long nItems, int rank) { alsSetModel(ctx, userIds, userFactors, nUsers, itemIds, itemFactors, nItems, rank); }
+    /** out: n float64, found: n bytes (0 = an id is not in the model). */
+    public void alsPredict(ByteBuffer u, ByteBuffer i, long n, ByteBuffer out, ByteBuffer found) { alsPredict(ctx, u, i, n, out, found); }
+
+    // ---- SVM (replaces svm.fit / weightsOption, SVMImpl.scala:29-34)
+    /** xDtype: 0 dense f32, 1 dense f64, 2 CSR (values f64, csrPtr int64, csrIdx int32).  w: dim float64 out. */
+    public void svmFit(ByteBuffer x, int xDtype, ByteBuffer csrPtr, ByteBuffer csrIdx, ByteBuffer y, long n, int dim,
+                       ByteBuffer blockId, int blocks, int iterations, long localIterations, double regularization,
+                       double stepsize, long seed, int rngMode, ByteBuffer w) {
+        svmFit(ctx, x, xDtype, csrPtr, csrIdx, y, n, dim, blockId, blocks, iterations, localIterations, regularization,
+               stepsize, seed, rngMode, w);
+    }
+    public void svmPredict(ByteBuffer x, int xDtype, ByteBuffer csrPtr, ByteBuffer csrIdx, long n, int dim, ByteBuffer w,
+                           double threshold, boolean outputDecisionFunction, ByteBuffer out) {
+        svmPredict(ctx, x, xDtype, csrPtr, csrIdx, n, dim, w, threshold, outputDecisionFunction, out);
+    }
+
+    private static native long create(int device);
+    private static native void destroy(long ctx);
+    private static native long[] alsFit(long ctx, ByteBuffer user, ByteBuffer item, ByteBuffer rating, long nnz, int rank,
+                                        int iterations, double lambda, long seed);
+    private static native void alsGetFactors(long ctx, int which, ByteBuffer ids, ByteBuffer factors);
+    private static native void alsSetModel(long ctx, ByteBuffer userIds, ByteBuffer userFactors, long nUsers, ByteBuffer itemIds,
+                                           ByteBuffer itemFactors, long nItems, int rank);
+    private static native void alsPredict(long ctx, ByteBuffer u, ByteBuffer i, long n, ByteBuffer out, ByteBuffer found);
+    private static native void svmFit(long ctx, ByteBuffer x, int xDtype, ByteBuffer csrPtr, ByteBuffer csrIdx, ByteBuffer y,
+                                      long n, int dim, ByteBuffer blockId, int blocks, int iterations, long localIterations,
+                                      double regularization, double stepsize, long seed, int rngMode, ByteBuffer w);
+    private static native void svmPredict(long ctx, ByteBuffer x, int xDtype, ByteBuffer csrPtr, ByteBuffer csrIdx, long n,
+                                          int dim, ByteBuffer w, double threshold, boolean outputDecisionFunction, ByteBuffer out);
+}

@@ -240,3 +240,33 @@ def test_sharded_half_steps_equal_unsharded(fms, ctx):
         _, Y = c.als_get_factors(1)
         assert np.array_equal(X, Xref) and np.array_equal(Y, Yref)             # same per-row math: bitwise equal
         c.close()
+
+
+def test_tensor_core_gramian_is_fp32_grade(fms, ctx):
+    """The tcgen05 kernel's system matrix (fp16 hi/lo split Gramian + lambda*n on the diagonal) and rhs, as the
+    solver warps receive them, against fp64 numpy: the split must deliver fp32-level accuracy (plain fp16 is 5e-4)."""
+    u, i, r = _case(fms, 400, 60, 12000, seed=3)
+    ctx.als_set_kernel(fms._native.ALS_KERNEL_AUTO)
+    ctx.als_load(u, i, r)
+    ctx.als_init(64, 42)
+    _, Y = ctx.als_get_factors(fms._native.ITEMS)
+    uid, iid = np.unique(u), np.unique(i)
+    G, b = ctx.debug_als_gramian(fms._native.USERS, 0.9, 0, 64)
+    for row in range(64):
+        sel = u == uid[row]
+        V = Y[np.searchsorted(iid, i[sel])]
+        Gr = V.T @ V + 0.9 * sel.sum() * np.eye(64)
+        br = V.T @ r[sel]
+        assert np.abs(G[row] - Gr).max() <= 2e-6 * np.abs(Gr).max()
+        assert np.abs(b[row] - br).max() <= 2e-6 * np.abs(br).max()
+
+
+def test_tensor_core_and_generic_kernels_agree_over_iterations(fms, ctx):
+    u, i, r = _case(fms, 3000, 500, 90_000, seed=12)
+    out = {}
+    for name, k in (("tc", fms._native.ALS_KERNEL_TC), ("generic", fms._native.ALS_KERNEL_GENERIC)):
+        ctx.als_set_kernel(k)
+        ctx.als_fit(u, i, r, 64, 4, 0.9, 42)
+        out[name] = (ctx.als_get_factors(0)[1], ctx.als_get_factors(1)[1])
+    ctx.als_set_kernel(fms._native.ALS_KERNEL_AUTO)
+    assert rel_err(out["tc"][0], out["generic"][0]) <= 5e-5 and rel_err(out["tc"][1], out["generic"][1]) <= 5e-5
