@@ -37,19 +37,27 @@ constexpr int D = 64;
 constexpr int KROWS = 16;                         // ratings per stage == K of one tcgen05.mma (fp16)
 constexpr int TILE_BYTES = KROWS * 128;           // one 64-wide operand chunk of one stage (two swizzle atoms)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // hi | lo | R | R'
-constexpr int NSTG = 8;                           // ring depth (64 KB, 32 KB of gathers in flight)
+constexpr int NSTG = 10;                          // ring depth (80 KB, 40 KB of gathers in flight)
 constexpr int NACC = 2;                           // TMEM accumulator slots of 256 columns
-constexpr int N_EPI = 4, N_SOLVE = 7, N_PROD = 4;
-constexpr int NGB = N_SOLVE;                      // one hand-off / L buffer per solver warp
-constexpr int GLD = 68;                           // row pitch of a hand-off buffer (floats)
-constexpr int W_EPI0 = 0, W_SOLVE0 = 4, W_MMA = 11, W_PROD0 = 12;
-constexpr int NWARPS = 16;
+constexpr int N_EPI = 4, N_SOLVE = 12, N_PROD = 7;
+constexpr int NGB = N_SOLVE;                      // one packed system / L buffer per solver warp
+constexpr int W_EPI0 = 0, W_SOLVE0 = 4, W_MMA = 16, W_PROD0 = 17;
+constexpr int NWARPS = 24;                        // 6 warpgroups: epilogue | 3 x solvers | MMA + producers x 2
+constexpr int REGS_EPI = 88, REGS_SOLVE = 104, REGS_AUX = 40;   // setmaxnreg budgets; must sum to the launch allocation (80 x 768)
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+
+// Packed lower-triangular column-major storage of a 64x64 system (and later of its Cholesky factor): column c holds
+// rows 4*(c/4) .. 63, so every column start and every 4-row group inside it is 16-byte aligned.
+constexpr int PK_FLOATS = 2176;
+__host__ __device__ constexpr int pk_off(int c) {                  // offset of column c (its first stored row is 4*(c/4))
+    return 256 * (c >> 2) - 8 * (c >> 2) * ((c >> 2) - 1) + (c & 3) * (64 - 4 * (c >> 2));
+}
+__host__ __device__ constexpr int pk_at(int i, int c) { return pk_off(c) + i - 4 * (c >> 2); }   // entry (i, c), i >= 4*(c/4)
 
 struct Smem {   // byte offsets from the 1024-aligned base
     static constexpr int ring = 0;
-    static constexpr int gbuf = ring + NSTG * STAGE_BYTES;                  // NGB x 64 x GLD floats
-    static constexpr int bsol = gbuf + NGB * D * GLD * 4;                   // NGB x 64 floats (rhs)
+    static constexpr int gbuf = ring + NSTG * STAGE_BYTES;                  // NGB x PK_FLOATS floats (+ slack for tail reads)
+    static constexpr int bsol = gbuf + NGB * PK_FLOATS * 4 + 512;           // NGB x 64 floats (rhs)
     static constexpr int invd = bsol + NGB * D * 4;                         // N_SOLVE x 64 floats (1 / L_jj)
     static constexpr int bars = invd + N_SOLVE * D * 4;
     static constexpr int n_bars = 2 * NSTG + 2 * NACC + 2 * NGB;
@@ -250,11 +258,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
     // this CTA owns the contiguous rows [first, last) == the stages [stage_ptr[first], stage_ptr[last])
     const int64_t first = cta_rows[blockIdx.x], last = cta_rows[blockIdx.x + 1];
 
-    if (warp >= W_PROD0) {
+    if (warp >= W_MMA) {
+      // warpgroups 4-5: tensor-core issuer + TMA producers need few registers
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
+      if (warp >= W_PROD0) {
         // ================================================================== producers: stage stream -> TMA gather4 + rating chunks
         // The ratings of a side are pre-laid as 16-entry stages (colp / valp, rows padded with the planes' zero row),
         // so a producer warp just streams: stage s of this CTA lives at [16 s, 16 s + 16).
@@ -299,7 +309,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             idx0 = idx1; rt0 = rt1;
             idx1 = idx2; rt1 = rt2;
         }
-    } else if (warp == W_MMA) {
+      } else {
         // ================================================================== MMA issuer
         uint32_t stage_ctr = 0, job = 0;
         const uint32_t id192 = make_idesc(192), id128 = make_idesc(128);
@@ -319,7 +329,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                              st == nst - 1 ? 1u : 0u);
             }
         }
+      }
     } else if (warp < W_SOLVE0) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
         // ================================================================== epilogue: TMEM -> registers -> hand-off buffer
         const int q = warp - W_EPI0;                              // TMEM lane quadrant == warp index % 4
         uint32_t job = 0;
@@ -330,26 +342,24 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             tc_fence_after();
             mbar_wait(bar_g_empty(g), ((job / NGB) & 1) ^ 1);
             float *bo = reinterpret_cast<float *>(sm + Smem::bsol + g * D * 4);
-            float *G = reinterpret_cast<float *>(sm + Smem::gbuf + g * D * GLD * 4);
+            float *G = reinterpret_cast<float *>(sm + Smem::gbuf + g * PK_FLOATS * 4);
             const int my_row = 16 * q + lane;                     // valid for lane < 16
             const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * 256u;
 #pragma unroll
             for (int c0 = 0; c0 < D; c0 += 32) {
+                if (c0 > 16 * q + 15) break;                       // this quadrant's rows have no lower-triangle entry there
                 float d1[32], d2[32];
                 tc_ld32(tq + c0, d1);
                 tc_ld32(tq + 64 + c0, d2);
                 if (lane < 16) {
 #pragma unroll
-                    for (int c = 0; c < 32; c += 4) {
-                        float4 o;
-                        o.x = fmaf(d2[c + 0], LO_INV, d1[c + 0]); o.y = fmaf(d2[c + 1], LO_INV, d1[c + 1]);
-                        o.z = fmaf(d2[c + 2], LO_INV, d1[c + 2]); o.w = fmaf(d2[c + 3], LO_INV, d1[c + 3]);
+                    for (int c = 0; c < 32; ++c) {
                         const int cc = c0 + c;
-                        if (my_row == cc + 0) o.x += reg;
-                        if (my_row == cc + 1) o.y += reg;
-                        if (my_row == cc + 2) o.z += reg;
-                        if (my_row == cc + 3) o.w += reg;
-                        *reinterpret_cast<float4 *>(G + my_row * GLD + cc) = o;
+                        if (cc <= my_row) {                        // lower triangle only, packed column-major
+                            float v = fmaf(d2[c], LO_INV, d1[c]);
+                            if (cc == my_row) v += reg;
+                            G[pk_off(cc) - 4 * (cc >> 2) + my_row] = v;
+                        }
                     }
                 }
             }
@@ -360,41 +370,49 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar_acc_empty(acc)); mbar_arrive(bar_g_full(g)); }
         }
-    } else if (warp < W_MMA) {
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOLVE));
         // ================================================================== solvers: one warp per system
+        // Lane l owns matrix rows l and l+32.  The system arrives packed (lower triangle, column-major) in this warp's
+        // private buffer, which then becomes the storage of L.  Right-looking Cholesky in rank-4 panels:
+        //   phase 1  columns  0..31 : rows l (cols 0..31) and l+32 (cols 0..31) in registers, two passes of four panels at
+        //                             static window positions
+        //   syrk     A22 -= L21 L21^T for row l+32 (cols 32..63), streamed from the buffer (keeps phase 1 at 64 data registers)
+        //   phase 2  columns 32..63 : row l+32 (cols 32..63) in registers, rotating window
+        //   back substitution, four columns at a time (column sweep); forward substitution is fused into the panels.
         const int sv = warp - W_SOLVE0;
         const int g = sv;
         float *invd = reinterpret_cast<float *>(sm + Smem::invd + sv * D * 4);
-        float *G = reinterpret_cast<float *>(sm + Smem::gbuf + g * D * GLD * 4);
+        float *Ls = reinterpret_cast<float *>(sm + Smem::gbuf + g * PK_FLOATS * 4);   // entry (i, c) at pk_at(i, c)
         const float *bi = reinterpret_cast<const float *>(sm + Smem::bsol + g * D * 4);
         uint32_t job = 0, use = 0;
         for (int64_t row = first; row < last; ++row, ++job) {
             if ((int)(job % N_SOLVE) != sv) continue;
             mbar_wait(bar_g_full(g), use & 1);
             ++use;
-            float2 A0[16], A1a[16], A1b[16];                      // row l cols 0..31 | row l+32 cols 0..31 | row l+32 cols 32..63
+            float2 A0[16], A1a[16];                               // row l cols 0..31 | row l+32 cols 0..31
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 x0 = *reinterpret_cast<const float4 *>(G + lane * GLD + 4 * c);
-                const float4 x1 = *reinterpret_cast<const float4 *>(G + (lane + 32) * GLD + 4 * c);
-                const float4 x2 = *reinterpret_cast<const float4 *>(G + (lane + 32) * GLD + 32 + 4 * c);
-                A0[2 * c] = make_float2(x0.x, x0.y); A0[2 * c + 1] = make_float2(x0.z, x0.w);
-                A1a[2 * c] = make_float2(x1.x, x1.y); A1a[2 * c + 1] = make_float2(x1.z, x1.w);
-                A1b[2 * c] = make_float2(x2.x, x2.y); A1b[2 * c + 1] = make_float2(x2.z, x2.w);
+            for (int w = 0; w < 16; ++w) {
+                const int c = 2 * w;
+                A0[w].x = (c <= lane) ? Ls[pk_off(c) - 4 * (c >> 2) + lane] : 0.f;
+                A0[w].y = (c + 1 <= lane) ? Ls[pk_off(c + 1) - 4 * ((c + 1) >> 2) + lane] : 0.f;
+                A1a[w].x = Ls[pk_off(c) - 4 * (c >> 2) + lane + 32];
+                A1a[w].y = Ls[pk_off(c + 1) - 4 * ((c + 1) >> 2) + lane + 32];
             }
             float b0 = bi[lane], b1 = bi[lane + 32];
             if (DUMP) {
                 float *o = dump + (int64_t)(row - row_begin) * (D * D + D);
-                for (int c = 0; c < D; ++c) { o[lane * D + c] = G[lane * GLD + c]; o[(lane + 32) * D + c] = G[(lane + 32) * GLD + c]; }
+                for (int c = 0; c < D; ++c) {                      // symmetric fill from the packed lower triangle
+                    const int i0 = lane, i1 = lane + 32;
+                    o[i0 * D + c] = (c <= i0) ? Ls[pk_at(i0, c)] : Ls[pk_at(c, i0)];
+                    o[i1 * D + c] = (c <= i1) ? Ls[pk_at(i1, c)] : Ls[pk_at(c, i1)];
+                }
                 o[D * D + lane] = b0; o[D * D + lane + 32] = b1;
             }
-            __syncwarp();                                         // every lane holds its rows: the buffer becomes L storage
-            float *Ls = G;                                        // Ls[j * GLD + i] = L[i][j]
+            __syncwarp();
             bool bad = false;
 
-            // ---------------- panels over columns 0..31 (pivot rows live in A0 / b0 of lanes j0..j0+3)
-            // Two passes over a 32-column register window; inside a pass the four panels sit at static window
-            // positions (no register rotation), between the passes the window moves down by 16 columns.
+            // ---------------- phase 1: panels over columns 0..31 (pivot rows live in A0 / b0 of lanes j0..j0+3)
 #pragma unroll 1
             for (int jw = 0; jw < 32; jw += 16) {
 #pragma unroll
@@ -418,18 +436,19 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                     b1 = fmaf(-q3, PF.z3, fmaf(-q2, PF.z2, fmaf(-q1, PF.z1, fmaf(-q0, PF.z0, b1))));
                     const int rel = lane - j0;
                     b0 = rel == 0 ? PF.z0 : rel == 1 ? PF.z1 : rel == 2 ? PF.z2 : rel == 3 ? PF.z3 : rel > 3 ? nb0 : b0;
-                    // publish the four L columns (column-major) and 1 / L_jj
-                    float *Lc = Ls + j0 * GLD;
-                    Lc[lane] = p0; Lc[GLD + lane] = p1; Lc[2 * GLD + lane] = p2; Lc[3 * GLD + lane] = p3;
-                    Lc[lane + 32] = q0; Lc[GLD + lane + 32] = q1; Lc[2 * GLD + lane + 32] = q2; Lc[3 * GLD + lane + 32] = q3;
+                    // publish the four L columns (rows >= j0 only: the packed columns start at row j0) and 1 / L_jj
+                    const int len = 64 - j0;                        // stored length of the panel's columns
+                    float *Lc = Ls + pk_off(0) + 256 * (j0 >> 2) - 8 * (j0 >> 2) * ((j0 >> 2) - 1) - j0;   // column j0, indexed by row
+                    if (lane >= j0) { Lc[lane] = p0; Lc[len + lane] = p1; Lc[2 * len + lane] = p2; Lc[3 * len + lane] = p3; }
+                    Lc[lane + 32] = q0; Lc[len + lane + 32] = q1; Lc[2 * len + lane + 32] = q2; Lc[3 * len + lane + 32] = q3;
                     if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(PF.i0, PF.i1, PF.i2, PF.i3);
                     __syncwarp();
-                    // trailing update of window positions P+2 .. 15 (columns j0+4 .. jw+31) and of columns 32..63
+                    // trailing update of window positions P+2 .. 15 (columns j0+4 .. jw+31)
                     const float pm[4] = {-p0, -p1, -p2, -p3}, qm[4] = {-q0, -q1, -q2, -q3};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const float2 pp = make_float2(pm[c], pm[c]), qq = make_float2(qm[c], qm[c]);
-                        const float *col_w = Lc + c * GLD + jw;                          // L[jw ..][j0+c]
+                        const float *col_w = Lc + c * len + jw;                          // L[jw ..][j0+c]
 #pragma unroll
                         for (int w = P + 2; w < 16; w += 2) {
                             const float4 lv = *reinterpret_cast<const float4 *>(col_w + 2 * w);
@@ -437,20 +456,34 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                             A0[w] = __ffma2_rn(pp, la, A0[w]); A0[w + 1] = __ffma2_rn(pp, lb, A0[w + 1]);
                             A1a[w] = __ffma2_rn(qq, la, A1a[w]); A1a[w + 1] = __ffma2_rn(qq, lb, A1a[w + 1]);
                         }
-                        const float *col_s = Lc + c * GLD + 32;                          // L[32 ..][j0+c]
-#pragma unroll
-                        for (int w4 = 0; w4 < 8; ++w4) {
-                            const float4 lv = *reinterpret_cast<const float4 *>(col_s + 4 * w4);
-                            A1b[2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A1b[2 * w4]);
-                            A1b[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A1b[2 * w4 + 1]);
-                        }
                     }
                 }
                 // move the window down by 16 columns (the vacated upper half only ever holds unused entries)
 #pragma unroll
                 for (int w = 0; w < 8; ++w) { A0[w] = A0[w + 8]; A1a[w] = A1a[w + 8]; }
             }
-            // ---------------- panels over columns 32..63 (pivot rows live in A1b / b1 of lanes j0-32 .. +3)
+            // ---------------- syrk: row l+32, columns 32..63:  A22[l+32][32+k] -= sum_{m<32} L[l+32][m] L[32+k][m]
+            float2 A1b[16];
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+                const int c = 32 + 2 * w;
+                A1b[w].x = (c <= lane + 32) ? Ls[pk_off(c) - 4 * (c >> 2) + lane + 32] : 0.f;
+                A1b[w].y = (c + 1 <= lane + 32) ? Ls[pk_off(c + 1) - 4 * ((c + 1) >> 2) + lane + 32] : 0.f;
+            }
+#pragma unroll 2
+            for (int m = 0; m < 32; ++m) {
+                const int gq = m >> 2, len = 64 - 4 * gq;
+                const float *colm = Ls + 256 * gq - 8 * gq * (gq - 1) + (m & 3) * len - 4 * gq;   // column m, indexed by row
+                const float own = -colm[lane + 32];
+                const float2 oo = make_float2(own, own);
+#pragma unroll
+                for (int w4 = 0; w4 < 8; ++w4) {
+                    const float4 lv = *reinterpret_cast<const float4 *>(colm + 32 + 4 * w4);
+                    A1b[2 * w4] = __ffma2_rn(oo, make_float2(lv.x, lv.y), A1b[2 * w4]);
+                    A1b[2 * w4 + 1] = __ffma2_rn(oo, make_float2(lv.z, lv.w), A1b[2 * w4 + 1]);
+                }
+            }
+            // ---------------- phase 2: panels over columns 32..63 (pivot rows live in A1b / b1 of lanes j0-32 .. +3)
 #pragma unroll 1
             for (int j0 = 32; j0 < 64; j0 += 4) {
                 const int src = j0 - 32;
@@ -469,16 +502,17 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                 const float nb1 = fmaf(-q3, P.z3, fmaf(-q2, P.z2, fmaf(-q1, P.z1, fmaf(-q0, P.z0, b1))));
                 const int rel = lane - src;
                 b1 = rel == 0 ? P.z0 : rel == 1 ? P.z1 : rel == 2 ? P.z2 : rel == 3 ? P.z3 : rel > 3 ? nb1 : b1;
-                float *Lc = Ls + j0 * GLD;
-                Lc[lane + 32] = q0; Lc[GLD + lane + 32] = q1; Lc[2 * GLD + lane + 32] = q2; Lc[3 * GLD + lane + 32] = q3;
+                const int gq = j0 >> 2, len = 64 - j0;
+                float *Lc = Ls + 256 * gq - 8 * gq * (gq - 1) - j0;                       // column j0, indexed by row
+                if (lane + 32 >= j0) { Lc[lane + 32] = q0; Lc[len + lane + 32] = q1; Lc[2 * len + lane + 32] = q2; Lc[3 * len + lane + 32] = q3; }
                 if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(P.i0, P.i1, P.i2, P.i3);
                 __syncwarp();
                 const float qm[4] = {-q0, -q1, -q2, -q3};
-                // columns beyond 63 read the neighbouring L column / padding: finite garbage that is never used
+                // rows beyond 63 read the neighbouring column / buffer: garbage that only lands in unused window entries
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float2 qq = make_float2(qm[c], qm[c]);
-                    const float *col_c = Lc + c * GLD + j0 + 4;
+                    const float *col_c = Lc + c * len + j0 + 4;
 #pragma unroll
                     for (int w4 = 0; w4 < 7; ++w4) {
                         const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
@@ -488,7 +522,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                 }
                 {
                     const float2 qq = make_float2(qm[3], qm[3]);
-                    const float *col_c = Lc + 3 * GLD + j0 + 4;
+                    const float *col_c = Lc + 3 * len + j0 + 4;
 #pragma unroll
                     for (int w4 = 0; w4 < 7; ++w4) {
                         const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
@@ -507,9 +541,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                 const float zsrc = hiside ? b1 : b0;
                 const float z0 = __shfl_sync(0xffffffffu, zsrc, src), z1 = __shfl_sync(0xffffffffu, zsrc, src + 1);
                 const float z2 = __shfl_sync(0xffffffffu, zsrc, src + 2), z3 = __shfl_sync(0xffffffffu, zsrc, src + 3);
-                const float4 c0 = *reinterpret_cast<const float4 *>(Ls + (j0 + 0) * GLD + j0);   // L[j0..j0+3][j0]
-                const float4 c1 = *reinterpret_cast<const float4 *>(Ls + (j0 + 1) * GLD + j0);   // L[..][j0+1]
-                const float4 c2 = *reinterpret_cast<const float4 *>(Ls + (j0 + 2) * GLD + j0);
+                const int gq = j0 >> 2, len = 64 - j0;
+                const float *Lc = Ls + 256 * gq - 8 * gq * (gq - 1);                     // column j0 starts at row j0
+                const float4 c0 = *reinterpret_cast<const float4 *>(Lc);                 // L[j0..j0+3][j0]
+                const float4 c1 = *reinterpret_cast<const float4 *>(Lc + len);           // L[j0..j0+3][j0+1]
+                const float4 c2 = *reinterpret_cast<const float4 *>(Lc + 2 * len);
                 const float4 iv = *reinterpret_cast<const float4 *>(invd + j0);
                 const float v3 = z3 * iv.w;
                 const float v2 = fmaf(-c2.w, v3, z2) * iv.z;
@@ -518,13 +554,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                 const int rel = lane - src;
                 const float mine = rel == 0 ? v0 : rel == 1 ? v1 : rel == 2 ? v2 : v3;
                 if (rel >= 0 && rel < 4) { if (hiside) x1 = mine; else x0 = mine; }
-                // z_i -= sum_c L[j0+c][i] x_c for the rows above the panel
+                // z_i -= sum_c L[j0+c][i] x_c for the rows above the panel: L[j0..j0+3][i] sits in column i at row j0
                 if (lane < j0) {
-                    const float4 lr = *reinterpret_cast<const float4 *>(Ls + lane * GLD + j0);   // L[j0..j0+3][lane]
+                    const int gi = lane >> 2;
+                    const float4 lr = *reinterpret_cast<const float4 *>(Ls + 256 * gi - 8 * gi * (gi - 1) + (lane & 3) * (64 - 4 * gi) + j0 - 4 * gi);
                     b0 = fmaf(-lr.w, v3, fmaf(-lr.z, v2, fmaf(-lr.y, v1, fmaf(-lr.x, v0, b0))));
                 }
                 if (lane + 32 < j0) {
-                    const float4 lr = *reinterpret_cast<const float4 *>(Ls + (lane + 32) * GLD + j0);
+                    const int i = lane + 32, gi = i >> 2;
+                    const float4 lr = *reinterpret_cast<const float4 *>(Ls + 256 * gi - 8 * gi * (gi - 1) + (i & 3) * (64 - 4 * gi) + j0 - 4 * gi);
                     b1 = fmaf(-lr.w, v3, fmaf(-lr.z, v2, fmaf(-lr.y, v1, fmaf(-lr.x, v0, b1))));
                 }
             }
