@@ -31,6 +31,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def full_config(args, world):
+    return world == 1 and (args.users, args.items, args.nnz, args.rank) == (1_000_000, 100_000, 100_000_000, 64)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -260,8 +270,10 @@ def main():
     dom_bytes, dom_ms = (by_user, ms_user) if dom == "users" else (by_item, ms_item)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     iter_gbs = (by_user + by_item) / (ms_step * 1e-3) / 1e9
+    traffic = load_traffic()
     roofline = {"bound": "hbm", "kernel": f"ALS half-step ({dom})", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic.get(f"als_half_step_{dom}") if full_config(args, world) else None,
+                "traffic_source": traffic.get("source"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                 "iteration": {"achieved": iter_gbs, "frac": iter_gbs / peak, "ms_users": ms_user, "ms_items": ms_item}}
     clocks = clk.summary()
@@ -361,7 +373,9 @@ def bench_svm(args, fms, D, synth, dev, rank, world, local_rank, peak, peak_src,
                                   f"K={K} blocks (block_id = i mod K), H = n_k (one epoch per round), lambda=1 "
                                   f"stepsize=1 seed=42", "l2": "X is 41 GB, far larger than L2"},
            "roofline": {"bound": "hbm", "kernel": "SVM block sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": achieved / peak,
+                        "traffic": load_traffic().get("svm_block_sweep") if (world == 1 and n == 10_000_000 and dim == 1024) else None,
+                        "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": svm_bytes_step(dim) * steps_per_rank, "ms_per_launch": ms},
            "gpu_launches": ctx.launch_count - l0, "train_accuracy_first_100k": acc, "clocks": clk.summary()}
     ctx.close()
