@@ -190,11 +190,15 @@ class Context:
     def als_factors_updated(self, which):
         self._check(self._lib.fms_als_factors_updated(self._h, which))
 
-    def als_get_factors(self, which):
+    def als_get_factors(self, which, ids_out=None, factors_out=None):
+        """ids_out / factors_out: optional caller buffers (e.g. numpy views of pinned memory, the analogue of a
+        registered direct ByteBuffer) of n int64 / n*rank float64; fresh pageable arrays otherwise."""
         nu, ni, rank = self._als_shape
         n = nu if which == USERS else ni
-        ids = np.empty(n, np.int64)
-        fac = np.empty((n, rank), np.float64)
+        ids = np.empty(n, np.int64) if ids_out is None else ids_out
+        fac = np.empty((n, rank), np.float64) if factors_out is None else factors_out
+        if ids.dtype != np.int64 or fac.dtype != np.float64 or ids.size < n or fac.size < n * rank or not fac.flags.c_contiguous:
+            raise ValueError("als_get_factors: output buffers have the wrong dtype / size")
         self._check(self._lib.fms_als_get_factors(self._h, which, _p(ids, _i64p), _p(fac, _f64p)))
         return ids, fac
 
