@@ -306,6 +306,22 @@ def main():
         assert np.isfinite(F_u).all() and np.isfinite(F_i).all()
     gpu_launches_als = launches
 
+    # ---------------------------------------------------------------------------------------- predict (configs[4])
+    predict = None
+    if rank == 0 and world == 1:
+        rng = np.random.default_rng(7)
+        nq = 1_000_000
+        qu = rng.integers(0, args.users, nq, dtype=np.int64)
+        qi = rng.integers(0, args.items, nq, dtype=np.int64)
+        ctx.als_predict(qu[:1000], qi[:1000])                                        # warm-up (fp64 model copy)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            out, found = ctx.als_predict(qu, qi)
+        dtp = (time.perf_counter() - t0) / 3
+        predict = {"metric": "als_lookups_per_sec", "value": nq / dtp, "unit": "lookups/s", "batch": nq,
+                   "found_fraction": float(found.mean()),
+                   "note": "fms_als_predict through the C-ABI: host ids in, H2D, id lookup + fp64 dot on device, D2H"}
+
     # ---------------------------------------------------------------------------------------- CPU baseline (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -332,7 +348,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": gpu_launches_als, "clocks": clocks, "svm": svm}
+                "gpu_launches": gpu_launches_als, "clocks": clocks, "svm": svm, "predict": predict}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -413,54 +413,60 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             bool bad = false;
 
             // ---------------- phase 1: panels over columns 0..31 (pivot rows live in A0 / b0 of lanes j0..j0+3)
+            // Rotating register window: positions 0..1 hold the panel's four columns, 2..15 the 28 columns behind it; the
+            // fourth update of a panel writes two positions down, which rotates the window without register moves.
 #pragma unroll 1
-            for (int jw = 0; jw < 32; jw += 16) {
+            for (int j0 = 0; j0 < 32; j0 += 4) {
+                const float d00 = __shfl_sync(0xffffffffu, A0[0].x, j0);
+                const float d10 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 1), d11 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 1);
+                const float d20 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 2), d21 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 2);
+                const float d22 = __shfl_sync(0xffffffffu, A0[1].x, j0 + 2);
+                const float d30 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 3), d31 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 3);
+                const float d32 = __shfl_sync(0xffffffffu, A0[1].x, j0 + 3), d33 = __shfl_sync(0xffffffffu, A0[1].y, j0 + 3);
+                const float zb0 = __shfl_sync(0xffffffffu, b0, j0), zb1 = __shfl_sync(0xffffffffu, b0, j0 + 1);
+                const float zb2 = __shfl_sync(0xffffffffu, b0, j0 + 2), zb3 = __shfl_sync(0xffffffffu, b0, j0 + 3);
+                const Panel PF = panel_factor(d00, d10, d11, d20, d21, d22, d30, d31, d32, d33, zb0, zb1, zb2, zb3);
+                bad |= PF.bad;
+                float p0, p1, p2, p3, q0, q1, q2, q3;
+                panel_row(PF, A0[0].x, A0[0].y, A0[1].x, A0[1].y, p0, p1, p2, p3);
+                panel_row(PF, A1a[0].x, A1a[0].y, A1a[1].x, A1a[1].y, q0, q1, q2, q3);
+                // rhs: rows below the panel get b_i -= sum_c L[i][c] z_c; pivot rows keep z; finished rows keep theirs
+                const float nb0 = fmaf(-p3, PF.z3, fmaf(-p2, PF.z2, fmaf(-p1, PF.z1, fmaf(-p0, PF.z0, b0))));
+                b1 = fmaf(-q3, PF.z3, fmaf(-q2, PF.z2, fmaf(-q1, PF.z1, fmaf(-q0, PF.z0, b1))));
+                const int rel = lane - j0;
+                b0 = rel == 0 ? PF.z0 : rel == 1 ? PF.z1 : rel == 2 ? PF.z2 : rel == 3 ? PF.z3 : rel > 3 ? nb0 : b0;
+                // publish the four L columns (rows >= j0 only: the packed columns start at row j0) and 1 / L_jj
+                const int gq = j0 >> 2, len = 64 - j0;
+                float *Lc = Ls + 256 * gq - 8 * gq * (gq - 1) - j0;                       // column j0, indexed by row
+                if (lane >= j0) { Lc[lane] = p0; Lc[len + lane] = p1; Lc[2 * len + lane] = p2; Lc[3 * len + lane] = p3; }
+                Lc[lane + 32] = q0; Lc[len + lane + 32] = q1; Lc[2 * len + lane + 32] = q2; Lc[3 * len + lane + 32] = q3;
+                if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(PF.i0, PF.i1, PF.i2, PF.i3);
+                __syncwarp();
+                const float pm[4] = {-p0, -p1, -p2, -p3}, qm[4] = {-q0, -q1, -q2, -q3};
+                // window columns beyond 31 read rows >= 32 of the L column: garbage that only lands in unused entries
 #pragma unroll
-                for (int P = 0; P < 8; P += 2) {                   // window position of the panel, in float2 units
-                    const int j0 = jw + 2 * P;
-                    const float d00 = __shfl_sync(0xffffffffu, A0[P].x, j0);
-                    const float d10 = __shfl_sync(0xffffffffu, A0[P].x, j0 + 1), d11 = __shfl_sync(0xffffffffu, A0[P].y, j0 + 1);
-                    const float d20 = __shfl_sync(0xffffffffu, A0[P].x, j0 + 2), d21 = __shfl_sync(0xffffffffu, A0[P].y, j0 + 2);
-                    const float d22 = __shfl_sync(0xffffffffu, A0[P + 1].x, j0 + 2);
-                    const float d30 = __shfl_sync(0xffffffffu, A0[P].x, j0 + 3), d31 = __shfl_sync(0xffffffffu, A0[P].y, j0 + 3);
-                    const float d32 = __shfl_sync(0xffffffffu, A0[P + 1].x, j0 + 3), d33 = __shfl_sync(0xffffffffu, A0[P + 1].y, j0 + 3);
-                    const float zb0 = __shfl_sync(0xffffffffu, b0, j0), zb1 = __shfl_sync(0xffffffffu, b0, j0 + 1);
-                    const float zb2 = __shfl_sync(0xffffffffu, b0, j0 + 2), zb3 = __shfl_sync(0xffffffffu, b0, j0 + 3);
-                    const Panel PF = panel_factor(d00, d10, d11, d20, d21, d22, d30, d31, d32, d33, zb0, zb1, zb2, zb3);
-                    bad |= PF.bad;
-                    float p0, p1, p2, p3, q0, q1, q2, q3;
-                    panel_row(PF, A0[P].x, A0[P].y, A0[P + 1].x, A0[P + 1].y, p0, p1, p2, p3);
-                    panel_row(PF, A1a[P].x, A1a[P].y, A1a[P + 1].x, A1a[P + 1].y, q0, q1, q2, q3);
-                    // rhs: rows below the panel get b_i -= sum_c L[i][c] z_c; pivot rows keep z; finished rows keep theirs
-                    const float nb0 = fmaf(-p3, PF.z3, fmaf(-p2, PF.z2, fmaf(-p1, PF.z1, fmaf(-p0, PF.z0, b0))));
-                    b1 = fmaf(-q3, PF.z3, fmaf(-q2, PF.z2, fmaf(-q1, PF.z1, fmaf(-q0, PF.z0, b1))));
-                    const int rel = lane - j0;
-                    b0 = rel == 0 ? PF.z0 : rel == 1 ? PF.z1 : rel == 2 ? PF.z2 : rel == 3 ? PF.z3 : rel > 3 ? nb0 : b0;
-                    // publish the four L columns (rows >= j0 only: the packed columns start at row j0) and 1 / L_jj
-                    const int len = 64 - j0;                        // stored length of the panel's columns
-                    float *Lc = Ls + pk_off(0) + 256 * (j0 >> 2) - 8 * (j0 >> 2) * ((j0 >> 2) - 1) - j0;   // column j0, indexed by row
-                    if (lane >= j0) { Lc[lane] = p0; Lc[len + lane] = p1; Lc[2 * len + lane] = p2; Lc[3 * len + lane] = p3; }
-                    Lc[lane + 32] = q0; Lc[len + lane + 32] = q1; Lc[2 * len + lane + 32] = q2; Lc[3 * len + lane + 32] = q3;
-                    if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(PF.i0, PF.i1, PF.i2, PF.i3);
-                    __syncwarp();
-                    // trailing update of window positions P+2 .. 15 (columns j0+4 .. jw+31)
-                    const float pm[4] = {-p0, -p1, -p2, -p3}, qm[4] = {-q0, -q1, -q2, -q3};
+                for (int c = 0; c < 3; ++c) {
+                    const float2 pp = make_float2(pm[c], pm[c]), qq = make_float2(qm[c], qm[c]);
+                    const float *col_c = Lc + c * len + j0 + 4;                          // L[j0+4 ..][j0+c]
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float2 pp = make_float2(pm[c], pm[c]), qq = make_float2(qm[c], qm[c]);
-                        const float *col_w = Lc + c * len + jw;                          // L[jw ..][j0+c]
-#pragma unroll
-                        for (int w = P + 2; w < 16; w += 2) {
-                            const float4 lv = *reinterpret_cast<const float4 *>(col_w + 2 * w);
-                            const float2 la = make_float2(lv.x, lv.y), lb = make_float2(lv.z, lv.w);
-                            A0[w] = __ffma2_rn(pp, la, A0[w]); A0[w + 1] = __ffma2_rn(pp, lb, A0[w + 1]);
-                            A1a[w] = __ffma2_rn(qq, la, A1a[w]); A1a[w + 1] = __ffma2_rn(qq, lb, A1a[w + 1]);
-                        }
+                    for (int w4 = 0; w4 < 7; ++w4) {
+                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
+                        const float2 la = make_float2(lv.x, lv.y), lb = make_float2(lv.z, lv.w);
+                        A0[2 + 2 * w4] = __ffma2_rn(pp, la, A0[2 + 2 * w4]); A0[3 + 2 * w4] = __ffma2_rn(pp, lb, A0[3 + 2 * w4]);
+                        A1a[2 + 2 * w4] = __ffma2_rn(qq, la, A1a[2 + 2 * w4]); A1a[3 + 2 * w4] = __ffma2_rn(qq, lb, A1a[3 + 2 * w4]);
                     }
                 }
-                // move the window down by 16 columns (the vacated upper half only ever holds unused entries)
+                {
+                    const float2 pp = make_float2(pm[3], pm[3]), qq = make_float2(qm[3], qm[3]);
+                    const float *col_c = Lc + 3 * len + j0 + 4;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) { A0[w] = A0[w + 8]; A1a[w] = A1a[w + 8]; }
+                    for (int w4 = 0; w4 < 7; ++w4) {
+                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
+                        const float2 la = make_float2(lv.x, lv.y), lb = make_float2(lv.z, lv.w);
+                        A0[2 * w4] = __ffma2_rn(pp, la, A0[2 + 2 * w4]); A0[2 * w4 + 1] = __ffma2_rn(pp, lb, A0[3 + 2 * w4]);
+                        A1a[2 * w4] = __ffma2_rn(qq, la, A1a[2 + 2 * w4]); A1a[2 * w4 + 1] = __ffma2_rn(qq, lb, A1a[3 + 2 * w4]);
+                    }
+                }
             }
             // ---------------- syrk: row l+32, columns 32..63:  A22[l+32][32+k] -= sum_{m<32} L[l+32][m] L[32+k][m]
             float2 A1b[16];
