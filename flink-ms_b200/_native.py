@@ -46,6 +46,8 @@ SIGNATURES = {
     "fms_als_half_step": (C.c_int, [_vp, C.c_int, C.c_double]),
     "fms_als_factors_device": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), _i64p, _i64p, _i64p]),
     "fms_als_factors_updated": (C.c_int, [_vp, C.c_int]),
+    "fms_als_planes_device": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _i64p]),
+    "fms_als_planes_updated": (C.c_int, [_vp, C.c_int]),
     "fms_als_last_info": (C.c_int, [_vp, _i64p]),
     "fms_als_set_kernel": (C.c_int, [_vp, C.c_int]),
     "fms_svm_fit": (C.c_int, [_vp, _vp, C.c_int, _i64p, _i32p, _f64p, C.c_int64, C.c_int32, _i32p, C.c_int, C.c_int,
@@ -186,6 +188,14 @@ class Context:
         ptr, rows, b, e = _vp(), C.c_int64(), C.c_int64(), C.c_int64()
         self._check(self._lib.fms_als_factors_device(self._h, which, C.byref(ptr), C.byref(rows), C.byref(b), C.byref(e)))
         return int(ptr.value or 0), rows.value, b.value, e.value
+
+    def als_planes_device(self, which):
+        hi, lo, rows = _vp(), _vp(), C.c_int64()
+        self._check(self._lib.fms_als_planes_device(self._h, which, C.byref(hi), C.byref(lo), C.byref(rows)))
+        return int(hi.value or 0), int(lo.value or 0), rows.value
+
+    def als_planes_updated(self, which):
+        self._check(self._lib.fms_als_planes_updated(self._h, which))
 
     def als_factors_updated(self, which):
         self._check(self._lib.fms_als_factors_updated(self._h, which))

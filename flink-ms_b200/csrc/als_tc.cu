@@ -782,6 +782,17 @@ int als_launch_half_step_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, i
     return launch_tc(ctx, which, lambda, rb, re, nullptr);
 }
 
+// device views of the gather planes of side `s` (allocated on demand) for plane-level exchange between ranks
+int als_tc_planes(fms_ctx *ctx, int s, void **hi, void **lo, int64_t *rows_padded) {
+    AlsState &A = ctx->als;
+    FMS_TRY(ensure_planes(ctx, s));
+    __half *h = reinterpret_cast<__half *>(A.plane[s].p);
+    if (hi) *hi = h;
+    if (lo) *lo = h + plane_rows(A, s) * tc::D;
+    if (rows_padded) *rows_padded = A.shard_rows[s] * A.shard_count;
+    return FMS_OK;
+}
+
 // test hook: system matrix + rhs of rows [rb, re) exactly as the solver warps receive them (row-major 64x64 + 64 floats each)
 int als_tc_dump(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t re, float *d_dump) {
     return launch_tc(ctx, which, lambda, rb, re, d_dump);

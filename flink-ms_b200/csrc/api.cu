@@ -184,6 +184,22 @@ FMS_API int fms_als_factors_updated(fms_ctx *ctx, int which) {
     return FMS_OK;
 }
 
+FMS_API int fms_als_planes_device(fms_ctx *ctx, int which, void **hi, void **lo, int64_t *rows_padded) {
+    CHECK_CTX(ctx);
+    AlsState &A = ctx->als;
+    if (!A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_planes_device: init first");
+    if (which != 0 && which != 1) return fail(ctx, FMS_ERR_INVALID_ARG, "which = %d", which);
+    if (!als_tc_supported(ctx, A.rank)) return fail(ctx, FMS_ERR_UNSUPPORTED, "no gather planes at rank %d", A.rank);
+    return als_tc_planes(ctx, which, hi, lo, rows_padded);
+}
+
+FMS_API int fms_als_planes_updated(fms_ctx *ctx, int which) {
+    if (!ctx) return FMS_ERR_INVALID_ARG;
+    if (which != 0 && which != 1) return fail(ctx, FMS_ERR_INVALID_ARG, "which = %d", which);
+    ctx->als.plane_valid[which] = true;      // every shard of the planes is current; the fp32 matrix may still be stale
+    return FMS_OK;
+}
+
 FMS_API int fms_als_fit(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t nnz, int rank,
                         int iterations, double lambda, int64_t seed, int64_t *n_users, int64_t *n_items) {
     CHECK_CTX(ctx);

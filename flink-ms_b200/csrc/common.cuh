@@ -102,6 +102,7 @@ struct SvmState {
     DevBuf<float> w;                         // dim
     DevBuf<float> dw_blocks;                 // blocks_local x dim partial deltas
     DevBuf<float> delta;                     // dim: sum over this rank's blocks
+    DevBuf<float> red_partial;               // two-level reduction scratch (chunks x dim)
     DevBuf<double> w64;                      // weights for the predict path
     bool w64_valid = false;
     int32_t w64_dim = 0;
@@ -213,6 +214,7 @@ int als_tc_supported(const fms_ctx *ctx, int rank);
 int als_launch_half_step_tc(fms_ctx *ctx, int which, float lambda, int64_t row_begin, int64_t row_end);
 int als_tc_refresh_planes(fms_ctx *ctx, int which);
 int als_tc_dump(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t re, float *d_dump);
+int als_tc_planes(fms_ctx *ctx, int s, void **hi, void **lo, int64_t *rows_padded);
 int als_predict_device(fms_ctx *ctx, const int64_t *d_u, const int64_t *d_i, int64_t n, double *d_out, uint8_t *d_found);
 int als_ensure_fac64(fms_ctx *ctx);
 int svm_launch_sweep(fms_ctx *ctx, int64_t local_iterations);

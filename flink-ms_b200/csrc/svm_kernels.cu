@@ -140,12 +140,26 @@ __global__ void __launch_bounds__(256) k_svm_sweep_generic_shared(
     if (threadIdx.x == 0) rng_state[0] = rng.s;
 }
 
-// delta[j] = sum over local blocks (ascending) of dw_blocks[k][j]
-__global__ void k_svm_reduce_delta(const float *__restrict__ dw_blocks, int n_local, int dim, float *__restrict__ delta) {
+// delta[j] = sum over local blocks of dw_blocks[k][j], in a FIXED two-level order (deterministic): the blocks are cut
+// into RED_CHUNKS contiguous chunks summed in ascending order by one thread each, then the chunk sums are added in
+// ascending chunk order.  (A single thread walking thousands of blocks per column was latency-bound.)
+constexpr int RED_CHUNKS = 64;
+__global__ void k_svm_reduce_partial(const float *__restrict__ dw_blocks, int n_local, int dim, float *__restrict__ partial) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (j >= dim) return;
+    const int per = (n_local + RED_CHUNKS - 1) / RED_CHUNKS;
+    const int k0 = c * per, k1 = min(n_local, k0 + per);
+    float s = 0.f;
+    for (int k = k0; k < k1; ++k) s += dw_blocks[(int64_t)k * dim + j];
+    partial[(int64_t)c * dim + j] = s;
+}
+__global__ void k_svm_reduce_delta(const float *__restrict__ partial, int dim, float *__restrict__ delta) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= dim) return;
     float s = 0.f;
-    for (int k = 0; k < n_local; ++k) s += dw_blocks[(int64_t)k * dim + j];
+#pragma unroll 8
+    for (int c = 0; c < RED_CHUNKS; ++c) s += partial[(int64_t)c * dim + j];
     delta[j] = s;
 }
 
@@ -209,7 +223,10 @@ int svm_launch_sweep(fms_ctx *ctx, int64_t local_iterations) {
 int svm_launch_reduce_delta(fms_ctx *ctx) {
     SvmState &S = ctx->svm;
     const int n_local = (int)S.local_blocks.size();
-    k_svm_reduce_delta<<<(S.dim + 255) / 256, 256, 0, ctx->stream>>>(S.dw_blocks.p, n_local, S.dim, S.delta.p);
+    FMS_CUDA(ctx, S.red_partial.alloc((size_t)RED_CHUNKS * S.dim));
+    k_svm_reduce_partial<<<dim3((S.dim + 127) / 128, RED_CHUNKS), 128, 0, ctx->stream>>>(S.dw_blocks.p, n_local, S.dim, S.red_partial.p);
+    FMS_LAUNCH_CHECK(ctx);
+    k_svm_reduce_delta<<<(S.dim + 127) / 128, 128, 0, ctx->stream>>>(S.red_partial.p, S.dim, S.delta.p);
     FMS_LAUNCH_CHECK(ctx);
     return FMS_OK;
 }

@@ -20,7 +20,7 @@ import torch.distributed as dist
 
 def device_view(ptr: int, numel: int, dtype=torch.float32, device="cuda:0") -> torch.Tensor:
     """Zero-copy torch view of `numel` elements at raw device address `ptr` (memory owned by the fms_ctx)."""
-    typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8"}[dtype]
+    typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8", torch.float16: "<f2"}[dtype]
 
     class _Iface:
         pass
@@ -55,6 +55,18 @@ class ContextALSBackend:
     def updated(self, which):
         self.ctx.als_factors_updated(which)
 
+    def plane_tensors(self, which, rank):
+        """(hi, lo) fp16 views of the gather planes, or None when the tensor-core path does not cover `rank`."""
+        try:
+            hi, lo, rows = self.ctx.als_planes_device(which)
+        except Exception:  # noqa: BLE001  (FMS_ERR_UNSUPPORTED: generic kernel in use)
+            return None
+        return (device_view(hi, rows * rank, torch.float16, self.device).view(rows, rank),
+                device_view(lo, rows * rank, torch.float16, self.device).view(rows, rank))
+
+    def planes_updated(self, which):
+        self.ctx.als_planes_updated(which)
+
 
 class DistributedALS:
     """iterate(T){ users = f(items); items = f(users) }; users = f(items), sharded by rows."""
@@ -64,11 +76,9 @@ class DistributedALS:
         self.rank_dim = rank_dim
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._stale = set()
 
-    def exchange(self, which):
-        if self.world == 1:
-            return
-        full = self.b.factor_tensor(which, self.rank_dim)               # (S * world, rank)
+    def _gather(self, full):
         s = full.shape[0] // self.world
         me = dist.get_rank(self.group)
         stream = getattr(self.b, "stream", None)
@@ -77,7 +87,28 @@ class DistributedALS:
                 dist.all_gather_into_tensor(full, full[me * s:(me + 1) * s], group=self.group)
         else:
             dist.all_gather_into_tensor(full, full[me * s:(me + 1) * s].clone(), group=self.group)
-        self.b.updated(which)
+
+    def exchange(self, which):
+        """All-gather what the next half-step reads.  With the tensor-core kernel that is the pair of fp16 gather
+        planes (same bytes as the fp32 rows, no re-split afterwards); the fp32 matrix is then gathered once in
+        finalize().  Otherwise the fp32 matrix itself."""
+        if self.world == 1:
+            return
+        planes = self.b.plane_tensors(which, self.rank_dim) if hasattr(self.b, "plane_tensors") else None
+        if planes is not None:
+            self._gather(planes[0])
+            self._gather(planes[1])
+            self.b.planes_updated(which)
+            self._stale.add(which)
+        else:
+            self._gather(self.b.factor_tensor(which, self.rank_dim))
+            self.b.updated(which)
+
+    def finalize(self):
+        """Bring every replica of the fp32 factor matrices up to date (needed before factors are read out)."""
+        for which in sorted(self._stale):
+            self._gather(self.b.factor_tensor(which, self.rank_dim))
+        self._stale.clear()
 
     def half_step(self, which, lam):
         self.b.half_step(which, lam)
@@ -91,6 +122,7 @@ class DistributedALS:
         for _ in range(iterations):
             self.iteration(lam)
         self.half_step(0, lam)
+        self.finalize()
 
 
 class ContextSVMBackend:
