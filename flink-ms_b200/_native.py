@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflinkms_b200.so")
+LIB_PATH = os.environ.get("FMS_LIB") or os.path.join(_HERE, "libflinkms_b200.so")   # FMS_LIB: A/B a differently built library
 
 OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_OOM = -1, -2, -3, -4, -5

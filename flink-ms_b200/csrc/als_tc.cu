@@ -37,13 +37,13 @@ constexpr int D = 64;
 constexpr int KROWS = 16;                         // ratings per stage == K of one tcgen05.mma (fp16)
 constexpr int TILE_BYTES = KROWS * 128;           // one 64-wide operand chunk of one stage (two swizzle atoms)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // hi | lo | R | R'
-constexpr int NSTG = 10;                          // ring depth (80 KB, 40 KB of gathers in flight)
+constexpr int NSTG = 8;                           // ring depth (64 KB, 32 KB of gathers in flight)
 constexpr int NACC = 2;                           // TMEM accumulator slots of 256 columns
-constexpr int N_EPI = 4, N_SOLVE = 12, N_PROD = 7;
+constexpr int N_EPI = 4, N_SOLVE = 16, N_PROD = 7;
 constexpr int NGB = N_SOLVE;                      // one packed system / L buffer per solver warp
-constexpr int W_EPI0 = 0, W_SOLVE0 = 4, W_MMA = 16, W_PROD0 = 17;
-constexpr int NWARPS = 24;                        // 6 warpgroups: epilogue | 3 x solvers | MMA + producers x 2
-constexpr int REGS_EPI = 88, REGS_SOLVE = 104, REGS_AUX = 40;   // setmaxnreg budgets; must sum to the launch allocation (80 x 768)
+constexpr int W_EPI0 = 0, W_SOLVE0 = 4, W_MMA = 20, W_PROD0 = 21;
+constexpr int NWARPS = 28;                        // 7 warpgroups: epilogue | 4 x solvers | MMA + producers x 2
+constexpr int REGS_EPI = 88, REGS_SOLVE = 80, REGS_AUX = 40;    // setmaxnreg budgets; sum <= launch allocation (72 x 896)
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
 // Packed lower-triangular column-major storage of a 64x64 system (and later of its Cholesky factor): column c holds
@@ -189,24 +189,21 @@ __device__ __forceinline__ void split_half(float x, __half &hi, __half &lo) {
 // 4x4 Cholesky of the pivot block + forward substitution of the panel's rhs (redundantly in every lane)
 struct Panel {
     float i0, i1, i2, i3, l10, l20, l30, l21, l31, l32, z0, z1, z2, z3;
-    bool bad;
 };
+// A non-positive pivot turns into NaN (rsqrt of a negative number, or 0 * inf in the refinement) and poisons the
+// solution, which is how breakdown is detected afterwards (LAPACK's info != 0; FlinkML ignores it, we count it).
 __device__ __forceinline__ Panel panel_factor(float d00, float d10, float d11, float d20, float d21, float d22, float d30, float d31,
                                               float d32, float d33, float zb0, float zb1, float zb2, float zb3) {
     Panel p;
-    p.bad = !(d00 > 0.f);
     p.i0 = rsqrt_refined(d00);
     p.l10 = d10 * p.i0; p.l20 = d20 * p.i0; p.l30 = d30 * p.i0;
     const float t11 = fmaf(-p.l10, p.l10, d11);
-    p.bad |= !(t11 > 0.f);
     p.i1 = rsqrt_refined(t11);
     p.l21 = fmaf(-p.l20, p.l10, d21) * p.i1; p.l31 = fmaf(-p.l30, p.l10, d31) * p.i1;
     const float t22 = fmaf(-p.l21, p.l21, fmaf(-p.l20, p.l20, d22));
-    p.bad |= !(t22 > 0.f);
     p.i2 = rsqrt_refined(t22);
     p.l32 = fmaf(-p.l31, p.l21, fmaf(-p.l30, p.l20, d32)) * p.i2;
     const float t33 = fmaf(-p.l32, p.l32, fmaf(-p.l31, p.l31, fmaf(-p.l30, p.l30, d33)));
-    p.bad |= !(t33 > 0.f);
     p.i3 = rsqrt_refined(t33);
     p.z0 = zb0 * p.i0;
     p.z1 = fmaf(-p.z0, p.l10, zb1) * p.i1;
@@ -220,6 +217,159 @@ __device__ __forceinline__ void panel_row(const Panel &p, float a0, float a1, fl
     x1 = fmaf(-x0, p.l10, a1) * p.i1;
     x2 = fmaf(-x1, p.l21, fmaf(-x0, p.l20, a2)) * p.i2;
     x3 = fmaf(-x2, p.l32, fmaf(-x1, p.l31, fmaf(-x0, p.l30, a3))) * p.i3;
+}
+
+__device__ __forceinline__ float fsel(int pred, float a, float b) {
+    float r;
+    asm("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\nselp.f32 %0, %1, %2, p;\n}\n" : "=f"(r) : "f"(a), "f"(b), "r"(pred));
+    return r;
+}
+// ---- solver building blocks (one matrix row per lane) -----------------------------------------------------------
+// Cholesky of one 32x32 diagonal block: lane l holds row (off + l) of the block, columns off .. off+31, in A[16]
+// (float2, rotating window: positions 0..1 are the current panel) and its rhs entry in b.  Rank-4 panels; the 4x4
+// pivot block is factored redundantly by every lane, its columns are published to the packed L storage and the
+// trailing window is updated with packed FFMA2 from broadcast LDS.128.  Forward substitution is fused (b -> z).
+__device__ __forceinline__ void chol32(float2 (&A)[16], float &b, float *Ls, float *invd, const int off, const int lane) {
+#pragma unroll 1
+    for (int jr = 0; jr < 32; jr += 4) {
+        const int j0 = off + jr;
+        const float d00 = __shfl_sync(0xffffffffu, A[0].x, jr);
+        const float d10 = __shfl_sync(0xffffffffu, A[0].x, jr + 1), d11 = __shfl_sync(0xffffffffu, A[0].y, jr + 1);
+        const float d20 = __shfl_sync(0xffffffffu, A[0].x, jr + 2), d21 = __shfl_sync(0xffffffffu, A[0].y, jr + 2);
+        const float d22 = __shfl_sync(0xffffffffu, A[1].x, jr + 2);
+        const float d30 = __shfl_sync(0xffffffffu, A[0].x, jr + 3), d31 = __shfl_sync(0xffffffffu, A[0].y, jr + 3);
+        const float d32 = __shfl_sync(0xffffffffu, A[1].x, jr + 3), d33 = __shfl_sync(0xffffffffu, A[1].y, jr + 3);
+        const float zb0 = __shfl_sync(0xffffffffu, b, jr), zb1 = __shfl_sync(0xffffffffu, b, jr + 1);
+        const float zb2 = __shfl_sync(0xffffffffu, b, jr + 2), zb3 = __shfl_sync(0xffffffffu, b, jr + 3);
+        const Panel P = panel_factor(d00, d10, d11, d20, d21, d22, d30, d31, d32, d33, zb0, zb1, zb2, zb3);
+        float q0, q1, q2, q3;
+        panel_row(P, A[0].x, A[0].y, A[1].x, A[1].y, q0, q1, q2, q3);
+        const float nb = fmaf(-q3, P.z3, fmaf(-q2, P.z2, fmaf(-q1, P.z1, fmaf(-q0, P.z0, b))));
+        const int rel = lane - jr;
+        const float zlo = fsel(rel & 1, P.z1, P.z0), zhi = fsel(rel & 1, P.z3, P.z2);
+        b = fsel(rel < 0, b, fsel(rel < 4, fsel(rel & 2, zhi, zlo), nb));                  // finished rows keep z; branch-free
+        const int gq = j0 >> 2, len = 64 - j0;
+        float *Lc = Ls + 256 * gq - 8 * gq * (gq - 1) - j0;                               // column j0, indexed by row
+        if (rel >= 0) { Lc[off + lane] = q0; Lc[len + off + lane] = q1; Lc[2 * len + off + lane] = q2; Lc[3 * len + off + lane] = q3; }
+        if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(P.i0, P.i1, P.i2, P.i3);
+        __syncwarp();
+        const float qm[4] = {-q0, -q1, -q2, -q3};
+        // window rows beyond the block read other columns / stale data: garbage that only lands in unused entries
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 qq = make_float2(qm[c], qm[c]);
+            const float *col_c = Lc + c * len + j0 + 4;
+#pragma unroll
+            for (int w4 = 0; w4 < 7; ++w4) {
+                const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
+                A[2 + 2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A[2 + 2 * w4]);
+                A[3 + 2 * w4] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A[3 + 2 * w4]);
+            }
+        }
+        {
+            const float2 qq = make_float2(qm[3], qm[3]);
+            const float *col_c = Lc + 3 * len + j0 + 4;
+#pragma unroll
+            for (int w4 = 0; w4 < 7; ++w4) {                     // the fourth update writes two positions down: window rotation
+                const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
+                A[2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A[2 + 2 * w4]);
+                A[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A[3 + 2 * w4]);
+            }
+        }
+    }
+}
+
+// Back substitution with one 32x32 diagonal block of L^T (column sweep, four columns at a time): on entry z holds
+// the block's rhs entry of this lane, on exit x.  Rows of the block are off + lane.
+__device__ __forceinline__ void backsub32(float &z, const float *Ls, const float *invd, const int off, const int lane) {
+    float x = 0.f;
+    const int i = off + lane, gi = i >> 2;
+    const float *coli = Ls + 256 * gi - 8 * gi * (gi - 1) + (i & 3) * (64 - 4 * gi) - 4 * gi;   // column i, indexed by row
+#pragma unroll 1
+    for (int jr = 28; jr >= 0; jr -= 4) {
+        const int j0 = off + jr;
+        const float z0 = __shfl_sync(0xffffffffu, z, jr), z1 = __shfl_sync(0xffffffffu, z, jr + 1);
+        const float z2 = __shfl_sync(0xffffffffu, z, jr + 2), z3 = __shfl_sync(0xffffffffu, z, jr + 3);
+        const int gq = j0 >> 2, len = 64 - j0;
+        const float *Lc = Ls + 256 * gq - 8 * gq * (gq - 1);                             // column j0 starts at row j0
+        const float4 c0 = *reinterpret_cast<const float4 *>(Lc);                         // L[j0..j0+3][j0]
+        const float4 c1 = *reinterpret_cast<const float4 *>(Lc + len);
+        const float4 c2 = *reinterpret_cast<const float4 *>(Lc + 2 * len);
+        const float4 iv = *reinterpret_cast<const float4 *>(invd + j0);
+        const float v3 = z3 * iv.w;
+        const float v2 = fmaf(-c2.w, v3, z2) * iv.z;
+        const float v1 = fmaf(-c1.w, v3, fmaf(-c1.z, v2, z1)) * iv.y;
+        const float v0 = fmaf(-c0.w, v3, fmaf(-c0.z, v2, fmaf(-c0.y, v1, z0))) * iv.x;
+        const int rel = lane - jr;
+        if (rel >= 0 && rel < 4) x = rel == 0 ? v0 : rel == 1 ? v1 : rel == 2 ? v2 : v3;
+        if (rel < 0) {                                           // rows above the panel: z_i -= sum_c L[j0+c][i] x_c
+            const float4 lr = *reinterpret_cast<const float4 *>(coli + j0);
+            z = fmaf(-lr.w, v3, fmaf(-lr.z, v2, fmaf(-lr.y, v1, fmaf(-lr.x, v0, z))));
+        }
+    }
+    z = x;
+}
+
+// L21 = A21 L11^-T for row 32+lane (a private triangular solve, no cross-lane traffic) with the rhs update, publication
+// of the row, then this lane's A22 row minus L21 L21^T.  On exit A holds row 32+lane of the updated A22.
+__device__ __forceinline__ void solver_trsm_syrk(float2 (&A)[16], float &b1, float *Ls, const float *invd, const float *bx, const int lane) {
+    // ---------------- trsm: row 32+l of L21 = A21 L11^-T, and b1 -= L21[row] . z1
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+        const int c = 2 * w;
+        A[w].x = Ls[pk_off(c) - 4 * (c >> 2) + lane + 32];
+        A[w].y = Ls[pk_off(c + 1) - 4 * ((c + 1) >> 2) + lane + 32];
+    }
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+        float4 iv4, z4;
+        if ((m & 3) == 0) { }
+        iv4 = *reinterpret_cast<const float4 *>(invd + (m & ~3));
+        z4 = *reinterpret_cast<const float4 *>(bx + (m & ~3));
+        const float ivm = (m & 3) == 0 ? iv4.x : (m & 3) == 1 ? iv4.y : (m & 3) == 2 ? iv4.z : iv4.w;
+        const float zm = (m & 3) == 0 ? z4.x : (m & 3) == 1 ? z4.y : (m & 3) == 2 ? z4.z : z4.w;
+        float &am = (m & 1) ? A[m >> 1].y : A[m >> 1].x;
+        const float xm = am * ivm;
+        am = xm;
+        b1 = fmaf(-xm, zm, b1);
+        const float2 xx = make_float2(-xm, -xm);
+        const float *colm = Ls + pk_off(m) - 4 * (m >> 2);                      // column m of L11, indexed by row
+#pragma unroll
+        for (int k4 = (m + 1) & ~3; k4 < 32; k4 += 4) {
+            const float4 lv = *reinterpret_cast<const float4 *>(colm + k4);
+            if (k4 > m) A[k4 >> 1] = __ffma2_rn(xx, make_float2(lv.x, lv.y), A[k4 >> 1]);
+            else if (k4 + 1 > m) A[k4 >> 1].y = fmaf(-xm, lv.y, A[k4 >> 1].y);
+            if (k4 + 2 > m) A[(k4 >> 1) + 1] = __ffma2_rn(xx, make_float2(lv.z, lv.w), A[(k4 >> 1) + 1]);
+            else if (k4 + 3 > m) A[(k4 >> 1) + 1].y = fmaf(-xm, lv.w, A[(k4 >> 1) + 1].y);
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {                         // publish row 32+l of L21
+        const int c = 2 * w;
+        Ls[pk_off(c) - 4 * (c >> 2) + lane + 32] = A[w].x;
+        Ls[pk_off(c + 1) - 4 * ((c + 1) >> 2) + lane + 32] = A[w].y;
+    }
+    __syncwarp();
+    // ---------------- syrk: A22[32+l][32+k] -= sum_{m<32} L21[l][m] L21[k][m]
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+        const int c = 32 + 2 * w;
+        A[w].x = (c <= lane + 32) ? Ls[pk_off(c) - 4 * (c >> 2) + lane + 32] : 0.f;
+        A[w].y = (c + 1 <= lane + 32) ? Ls[pk_off(c + 1) - 4 * ((c + 1) >> 2) + lane + 32] : 0.f;
+    }
+#pragma unroll 2
+    for (int m = 0; m < 32; ++m) {
+        const int gq = m >> 2, len = 64 - 4 * gq;
+        const float *colm = Ls + 256 * gq - 8 * gq * (gq - 1) + (m & 3) * len - 4 * gq;   // column m, indexed by row
+        const float own = -colm[lane + 32];
+        const float2 oo = make_float2(own, own);
+#pragma unroll
+        for (int w4 = 0; w4 < 8; ++w4) {
+            const float4 lv = *reinterpret_cast<const float4 *>(colm + 32 + 4 * w4);
+            A[2 * w4] = __ffma2_rn(oo, make_float2(lv.x, lv.y), A[2 * w4]);
+            A[2 * w4 + 1] = __ffma2_rn(oo, make_float2(lv.z, lv.w), A[2 * w4 + 1]);
+        }
+    }
 }
 
 template <bool DUMP>
@@ -373,33 +523,23 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOLVE));
         // ================================================================== solvers: one warp per system
-        // Lane l owns matrix rows l and l+32.  The system arrives packed (lower triangle, column-major) in this warp's
-        // private buffer, which then becomes the storage of L.  Right-looking Cholesky in rank-4 panels:
-        //   phase 1  columns  0..31 : rows l (cols 0..31) and l+32 (cols 0..31) in registers, two passes of four panels at
-        //                             static window positions
-        //   syrk     A22 -= L21 L21^T for row l+32 (cols 32..63), streamed from the buffer (keeps phase 1 at 64 data registers)
-        //   phase 2  columns 32..63 : row l+32 (cols 32..63) in registers, rotating window
-        //   back substitution, four columns at a time (column sweep); forward substitution is fused into the panels.
+        // The system arrives packed (lower triangle, column-major) in this warp's private buffer, which then becomes the
+        // storage of L.  With A = [A11 .; A21 A22] in 32x32 blocks and ONE matrix row per lane at a time:
+        //   chol32(A11)  ->  L11, z1          (lane = row l, 32 registers of matrix data)
+        //   trsm         ->  L21 = A21 L11^-T (lane = row 32+l; a private triangular solve per row: no shuffles, no barriers)
+        //   syrk         ->  A22 -= L21 L21^T (lane = row 32+l)
+        //   chol32(A22)  ->  L22, z2
+        //   back substitution: x2 from L22^T, z1 -= L21^T x2, x1 from L11^T.
         const int sv = warp - W_SOLVE0;
         const int g = sv;
         float *invd = reinterpret_cast<float *>(sm + Smem::invd + sv * D * 4);
         float *Ls = reinterpret_cast<float *>(sm + Smem::gbuf + g * PK_FLOATS * 4);   // entry (i, c) at pk_at(i, c)
-        const float *bi = reinterpret_cast<const float *>(sm + Smem::bsol + g * D * 4);
-        uint32_t job = 0, use = 0;
-        for (int64_t row = first; row < last; ++row, ++job) {
-            if ((int)(job % N_SOLVE) != sv) continue;
+        float *bx = reinterpret_cast<float *>(sm + Smem::bsol + g * D * 4);           // rhs in; scratch for z1 / x2 afterwards
+        uint32_t use = 0;
+        for (int64_t row = first + sv; row < last; row += N_SOLVE) {
             mbar_wait(bar_g_full(g), use & 1);
             ++use;
-            float2 A0[16], A1a[16];                               // row l cols 0..31 | row l+32 cols 0..31
-#pragma unroll
-            for (int w = 0; w < 16; ++w) {
-                const int c = 2 * w;
-                A0[w].x = (c <= lane) ? Ls[pk_off(c) - 4 * (c >> 2) + lane] : 0.f;
-                A0[w].y = (c + 1 <= lane) ? Ls[pk_off(c + 1) - 4 * ((c + 1) >> 2) + lane] : 0.f;
-                A1a[w].x = Ls[pk_off(c) - 4 * (c >> 2) + lane + 32];
-                A1a[w].y = Ls[pk_off(c + 1) - 4 * ((c + 1) >> 2) + lane + 32];
-            }
-            float b0 = bi[lane], b1 = bi[lane + 32];
+            float b0 = bx[lane], b1 = bx[lane + 32];
             if (DUMP) {
                 float *o = dump + (int64_t)(row - row_begin) * (D * D + D);
                 for (int c = 0; c < D; ++c) {                      // symmetric fill from the packed lower triangle
@@ -409,179 +549,60 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                 }
                 o[D * D + lane] = b0; o[D * D + lane + 32] = b1;
             }
-            __syncwarp();
-            bool bad = false;
-
-            // ---------------- phase 1: panels over columns 0..31 (pivot rows live in A0 / b0 of lanes j0..j0+3)
-            // Rotating register window: positions 0..1 hold the panel's four columns, 2..15 the 28 columns behind it; the
-            // fourth update of a panel writes two positions down, which rotates the window without register moves.
+            float2 A[16];
+            float bc = b0, z1 = 0.f;
 #pragma unroll 1
-            for (int j0 = 0; j0 < 32; j0 += 4) {
-                const float d00 = __shfl_sync(0xffffffffu, A0[0].x, j0);
-                const float d10 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 1), d11 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 1);
-                const float d20 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 2), d21 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 2);
-                const float d22 = __shfl_sync(0xffffffffu, A0[1].x, j0 + 2);
-                const float d30 = __shfl_sync(0xffffffffu, A0[0].x, j0 + 3), d31 = __shfl_sync(0xffffffffu, A0[0].y, j0 + 3);
-                const float d32 = __shfl_sync(0xffffffffu, A0[1].x, j0 + 3), d33 = __shfl_sync(0xffffffffu, A0[1].y, j0 + 3);
-                const float zb0 = __shfl_sync(0xffffffffu, b0, j0), zb1 = __shfl_sync(0xffffffffu, b0, j0 + 1);
-                const float zb2 = __shfl_sync(0xffffffffu, b0, j0 + 2), zb3 = __shfl_sync(0xffffffffu, b0, j0 + 3);
-                const Panel PF = panel_factor(d00, d10, d11, d20, d21, d22, d30, d31, d32, d33, zb0, zb1, zb2, zb3);
-                bad |= PF.bad;
-                float p0, p1, p2, p3, q0, q1, q2, q3;
-                panel_row(PF, A0[0].x, A0[0].y, A0[1].x, A0[1].y, p0, p1, p2, p3);
-                panel_row(PF, A1a[0].x, A1a[0].y, A1a[1].x, A1a[1].y, q0, q1, q2, q3);
-                // rhs: rows below the panel get b_i -= sum_c L[i][c] z_c; pivot rows keep z; finished rows keep theirs
-                const float nb0 = fmaf(-p3, PF.z3, fmaf(-p2, PF.z2, fmaf(-p1, PF.z1, fmaf(-p0, PF.z0, b0))));
-                b1 = fmaf(-q3, PF.z3, fmaf(-q2, PF.z2, fmaf(-q1, PF.z1, fmaf(-q0, PF.z0, b1))));
-                const int rel = lane - j0;
-                b0 = rel == 0 ? PF.z0 : rel == 1 ? PF.z1 : rel == 2 ? PF.z2 : rel == 3 ? PF.z3 : rel > 3 ? nb0 : b0;
-                // publish the four L columns (rows >= j0 only: the packed columns start at row j0) and 1 / L_jj
-                const int gq = j0 >> 2, len = 64 - j0;
-                float *Lc = Ls + 256 * gq - 8 * gq * (gq - 1) - j0;                       // column j0, indexed by row
-                if (lane >= j0) { Lc[lane] = p0; Lc[len + lane] = p1; Lc[2 * len + lane] = p2; Lc[3 * len + lane] = p3; }
-                Lc[lane + 32] = q0; Lc[len + lane + 32] = q1; Lc[2 * len + lane + 32] = q2; Lc[3 * len + lane + 32] = q3;
-                if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(PF.i0, PF.i1, PF.i2, PF.i3);
-                __syncwarp();
-                const float pm[4] = {-p0, -p1, -p2, -p3}, qm[4] = {-q0, -q1, -q2, -q3};
-                // window columns beyond 31 read rows >= 32 of the L column: garbage that only lands in unused entries
+            for (int h = 0; h < 2; ++h) {
+                if (h == 0) {
+                    // ---------------- A11: row l, columns 0..31
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float2 pp = make_float2(pm[c], pm[c]), qq = make_float2(qm[c], qm[c]);
-                    const float *col_c = Lc + c * len + j0 + 4;                          // L[j0+4 ..][j0+c]
-#pragma unroll
-                    for (int w4 = 0; w4 < 7; ++w4) {
-                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
-                        const float2 la = make_float2(lv.x, lv.y), lb = make_float2(lv.z, lv.w);
-                        A0[2 + 2 * w4] = __ffma2_rn(pp, la, A0[2 + 2 * w4]); A0[3 + 2 * w4] = __ffma2_rn(pp, lb, A0[3 + 2 * w4]);
-                        A1a[2 + 2 * w4] = __ffma2_rn(qq, la, A1a[2 + 2 * w4]); A1a[3 + 2 * w4] = __ffma2_rn(qq, lb, A1a[3 + 2 * w4]);
+                    for (int w = 0; w < 16; ++w) {
+                        const int c = 2 * w;
+                        A[w].x = (c <= lane) ? Ls[pk_off(c) - 4 * (c >> 2) + lane] : 0.f;
+                        A[w].y = (c + 1 <= lane) ? Ls[pk_off(c + 1) - 4 * ((c + 1) >> 2) + lane] : 0.f;
                     }
+                    __syncwarp();
+                } else {
+                    solver_trsm_syrk(A, bc, Ls, invd, bx, lane);
                 }
-                {
-                    const float2 pp = make_float2(pm[3], pm[3]), qq = make_float2(qm[3], qm[3]);
-                    const float *col_c = Lc + 3 * len + j0 + 4;
-#pragma unroll
-                    for (int w4 = 0; w4 < 7; ++w4) {
-                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
-                        const float2 la = make_float2(lv.x, lv.y), lb = make_float2(lv.z, lv.w);
-                        A0[2 * w4] = __ffma2_rn(pp, la, A0[2 + 2 * w4]); A0[2 * w4 + 1] = __ffma2_rn(pp, lb, A0[3 + 2 * w4]);
-                        A1a[2 * w4] = __ffma2_rn(qq, la, A1a[2 + 2 * w4]); A1a[2 * w4 + 1] = __ffma2_rn(qq, lb, A1a[3 + 2 * w4]);
-                    }
+                chol32(A, bc, Ls, invd, 32 * h, lane);
+                if (h == 0) {
+                    z1 = bc;
+                    bx[lane] = z1;                                 // z1, broadcast source for the trsm rhs update
+                    __syncwarp();
+                    bc = b1;
                 }
             }
-            // ---------------- syrk: row l+32, columns 32..63:  A22[l+32][32+k] -= sum_{m<32} L[l+32][m] L[32+k][m]
-            float2 A1b[16];
-#pragma unroll
-            for (int w = 0; w < 16; ++w) {
-                const int c = 32 + 2 * w;
-                A1b[w].x = (c <= lane + 32) ? Ls[pk_off(c) - 4 * (c >> 2) + lane + 32] : 0.f;
-                A1b[w].y = (c + 1 <= lane + 32) ? Ls[pk_off(c + 1) - 4 * ((c + 1) >> 2) + lane + 32] : 0.f;
-            }
-#pragma unroll 2
-            for (int m = 0; m < 32; ++m) {
-                const int gq = m >> 2, len = 64 - 4 * gq;
-                const float *colm = Ls + 256 * gq - 8 * gq * (gq - 1) + (m & 3) * len - 4 * gq;   // column m, indexed by row
-                const float own = -colm[lane + 32];
-                const float2 oo = make_float2(own, own);
-#pragma unroll
-                for (int w4 = 0; w4 < 8; ++w4) {
-                    const float4 lv = *reinterpret_cast<const float4 *>(colm + 32 + 4 * w4);
-                    A1b[2 * w4] = __ffma2_rn(oo, make_float2(lv.x, lv.y), A1b[2 * w4]);
-                    A1b[2 * w4 + 1] = __ffma2_rn(oo, make_float2(lv.z, lv.w), A1b[2 * w4 + 1]);
-                }
-            }
-            // ---------------- phase 2: panels over columns 32..63 (pivot rows live in A1b / b1 of lanes j0-32 .. +3)
-#pragma unroll 1
-            for (int j0 = 32; j0 < 64; j0 += 4) {
-                const int src = j0 - 32;
-                const float d00 = __shfl_sync(0xffffffffu, A1b[0].x, src);
-                const float d10 = __shfl_sync(0xffffffffu, A1b[0].x, src + 1), d11 = __shfl_sync(0xffffffffu, A1b[0].y, src + 1);
-                const float d20 = __shfl_sync(0xffffffffu, A1b[0].x, src + 2), d21 = __shfl_sync(0xffffffffu, A1b[0].y, src + 2);
-                const float d22 = __shfl_sync(0xffffffffu, A1b[1].x, src + 2);
-                const float d30 = __shfl_sync(0xffffffffu, A1b[0].x, src + 3), d31 = __shfl_sync(0xffffffffu, A1b[0].y, src + 3);
-                const float d32 = __shfl_sync(0xffffffffu, A1b[1].x, src + 3), d33 = __shfl_sync(0xffffffffu, A1b[1].y, src + 3);
-                const float zb0 = __shfl_sync(0xffffffffu, b1, src), zb1 = __shfl_sync(0xffffffffu, b1, src + 1);
-                const float zb2 = __shfl_sync(0xffffffffu, b1, src + 2), zb3 = __shfl_sync(0xffffffffu, b1, src + 3);
-                const Panel P = panel_factor(d00, d10, d11, d20, d21, d22, d30, d31, d32, d33, zb0, zb1, zb2, zb3);
-                bad |= P.bad;
-                float q0, q1, q2, q3;
-                panel_row(P, A1b[0].x, A1b[0].y, A1b[1].x, A1b[1].y, q0, q1, q2, q3);
-                const float nb1 = fmaf(-q3, P.z3, fmaf(-q2, P.z2, fmaf(-q1, P.z1, fmaf(-q0, P.z0, b1))));
-                const int rel = lane - src;
-                b1 = rel == 0 ? P.z0 : rel == 1 ? P.z1 : rel == 2 ? P.z2 : rel == 3 ? P.z3 : rel > 3 ? nb1 : b1;
-                const int gq = j0 >> 2, len = 64 - j0;
-                float *Lc = Ls + 256 * gq - 8 * gq * (gq - 1) - j0;                       // column j0, indexed by row
-                if (lane + 32 >= j0) { Lc[lane + 32] = q0; Lc[len + lane + 32] = q1; Lc[2 * len + lane + 32] = q2; Lc[3 * len + lane + 32] = q3; }
-                if (lane == 0) *reinterpret_cast<float4 *>(invd + j0) = make_float4(P.i0, P.i1, P.i2, P.i3);
-                __syncwarp();
-                const float qm[4] = {-q0, -q1, -q2, -q3};
-                // rows beyond 63 read the neighbouring column / buffer: garbage that only lands in unused window entries
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float2 qq = make_float2(qm[c], qm[c]);
-                    const float *col_c = Lc + c * len + j0 + 4;
-#pragma unroll
-                    for (int w4 = 0; w4 < 7; ++w4) {
-                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
-                        A1b[2 + 2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A1b[2 + 2 * w4]);
-                        A1b[3 + 2 * w4] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A1b[3 + 2 * w4]);
-                    }
-                }
-                {
-                    const float2 qq = make_float2(qm[3], qm[3]);
-                    const float *col_c = Lc + 3 * len + j0 + 4;
-#pragma unroll
-                    for (int w4 = 0; w4 < 7; ++w4) {
-                        const float4 lv = *reinterpret_cast<const float4 *>(col_c + 4 * w4);
-                        A1b[2 * w4] = __ffma2_rn(qq, make_float2(lv.x, lv.y), A1b[2 + 2 * w4]);
-                        A1b[2 * w4 + 1] = __ffma2_rn(qq, make_float2(lv.z, lv.w), A1b[3 + 2 * w4]);
-                    }
-                }
-            }
+            b0 = z1; b1 = bc;
+            // ---------------- back substitution
+            backsub32(b1, Ls, invd, 32, lane);                     // b1 = x[32+l]
+            bx[32 + lane] = b1;
             __syncwarp();
-            // ---------------- back substitution L^T x = z, four columns at a time (column sweep): b0 / b1 hold z
-            float x0 = 0.f, x1 = 0.f;
-#pragma unroll 1
-            for (int j0 = D - 4; j0 >= 0; j0 -= 4) {
-                const bool hiside = j0 >= 32;                      // pivot rows live in b1 (lanes j0-32..) or b0 (lanes j0..)
-                const int src = hiside ? j0 - 32 : j0;
-                const float zsrc = hiside ? b1 : b0;
-                const float z0 = __shfl_sync(0xffffffffu, zsrc, src), z1 = __shfl_sync(0xffffffffu, zsrc, src + 1);
-                const float z2 = __shfl_sync(0xffffffffu, zsrc, src + 2), z3 = __shfl_sync(0xffffffffu, zsrc, src + 3);
-                const int gq = j0 >> 2, len = 64 - j0;
-                const float *Lc = Ls + 256 * gq - 8 * gq * (gq - 1);                     // column j0 starts at row j0
-                const float4 c0 = *reinterpret_cast<const float4 *>(Lc);                 // L[j0..j0+3][j0]
-                const float4 c1 = *reinterpret_cast<const float4 *>(Lc + len);           // L[j0..j0+3][j0+1]
-                const float4 c2 = *reinterpret_cast<const float4 *>(Lc + 2 * len);
-                const float4 iv = *reinterpret_cast<const float4 *>(invd + j0);
-                const float v3 = z3 * iv.w;
-                const float v2 = fmaf(-c2.w, v3, z2) * iv.z;
-                const float v1 = fmaf(-c1.w, v3, fmaf(-c1.z, v2, z1)) * iv.y;
-                const float v0 = fmaf(-c0.w, v3, fmaf(-c0.z, v2, fmaf(-c0.y, v1, z0))) * iv.x;
-                const int rel = lane - src;
-                const float mine = rel == 0 ? v0 : rel == 1 ? v1 : rel == 2 ? v2 : v3;
-                if (rel >= 0 && rel < 4) { if (hiside) x1 = mine; else x0 = mine; }
-                // z_i -= sum_c L[j0+c][i] x_c for the rows above the panel: L[j0..j0+3][i] sits in column i at row j0
-                if (lane < j0) {
-                    const int gi = lane >> 2;
-                    const float4 lr = *reinterpret_cast<const float4 *>(Ls + 256 * gi - 8 * gi * (gi - 1) + (lane & 3) * (64 - 4 * gi) + j0 - 4 * gi);
-                    b0 = fmaf(-lr.w, v3, fmaf(-lr.z, v2, fmaf(-lr.y, v1, fmaf(-lr.x, v0, b0))));
+            {                                                      // z1[l] -= sum_i L21[i][l] x2[i]
+                const int gi = lane >> 2;
+                const float *coll = Ls + 256 * gi - 8 * gi * (gi - 1) + (lane & 3) * (64 - 4 * gi) - 4 * gi + 32;   // column l, rows 32..
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const float4 lv = *reinterpret_cast<const float4 *>(coll + 4 * t);
+                    const float4 xv = *reinterpret_cast<const float4 *>(bx + 32 + 4 * t);
+                    acc = __ffma2_rn(make_float2(lv.x, lv.y), make_float2(xv.x, xv.y), acc);
+                    acc = __ffma2_rn(make_float2(lv.z, lv.w), make_float2(xv.z, xv.w), acc);
                 }
-                if (lane + 32 < j0) {
-                    const int i = lane + 32, gi = i >> 2;
-                    const float4 lr = *reinterpret_cast<const float4 *>(Ls + 256 * gi - 8 * gi * (gi - 1) + (i & 3) * (64 - 4 * gi) + j0 - 4 * gi);
-                    b1 = fmaf(-lr.w, v3, fmaf(-lr.z, v2, fmaf(-lr.y, v1, fmaf(-lr.x, v0, b1))));
-                }
+                b0 -= acc.x + acc.y;
             }
+            backsub32(b0, Ls, invd, 0, lane);                      // b0 = x[l]
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_g_empty(g));           // L storage no longer needed
-            T[row * D + lane] = x0;
-            T[row * D + lane + 32] = x1;
+            if (lane == 0) mbar_arrive(bar_g_empty(g));           // L storage / scratch no longer needed
+            T[row * D + lane] = b0;
+            T[row * D + lane + 32] = b1;
             __half h0, l0, h1, l1;
-            split_half(x0, h0, l0);
-            split_half(x1, h1, l1);
+            split_half(b0, h0, l0);
+            split_half(b1, h1, l1);
             T_hi[row * D + lane] = h0; T_hi[row * D + lane + 32] = h1;
             T_lo[row * D + lane] = l0; T_lo[row * D + lane + 32] = l1;
-            if (bad && lane == 0) atomicAdd(info, 1);
+            const bool bad = !(fabsf(b0) <= 3.0e38f) || !(fabsf(b1) <= 3.0e38f);                 // NaN / inf: the factorisation broke down
+            if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(info, 1);
         }
     }
     tc_fence_before();
