@@ -37,7 +37,7 @@ constexpr int D = 64;
 constexpr int KROWS = 16;                         // ratings per stage == K of one tcgen05.mma (fp16)
 constexpr int TILE_BYTES = KROWS * 128;           // one 64-wide operand chunk of one stage (two swizzle atoms)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // hi | lo | R | R'
-constexpr int NSTG = 8;                           // ring depth (64 KB, 32 KB of gathers in flight)
+constexpr int NSTG = 10;                          // ring depth (80 KB, 40 KB of gathers in flight)
 constexpr int NACC = 2;                           // TMEM accumulator slots of 256 columns
 constexpr int N_EPI = 4, N_SOLVE = 16, N_PROD = 7;
 constexpr int NGB = N_SOLVE;                      // one packed system / L buffer per solver warp
