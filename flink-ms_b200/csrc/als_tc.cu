@@ -38,7 +38,11 @@ constexpr int KROWS = 16;                         // ratings per stage == K of o
 constexpr int TILE_BYTES = KROWS * 128;           // one 64-wide operand chunk of one stage (two swizzle atoms)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // hi | lo | R | R'
 constexpr int NSTG = 10;                          // ring depth (80 KB, 40 KB of gathers in flight)
-constexpr int NACC = 2;                           // TMEM accumulator slots of 256 columns
+constexpr int NACC = 2;                           // TMEM accumulator slots
+constexpr uint32_t ACC_COLS = 256u;               // TMEM columns per slot (136 used)
+// MMA widths: the first covers hi | lo | 8 rating columns, the second hi | 8 rating columns.  Only two rating columns
+// carry data; N = 136 / 72 instead of three / two full 64-wide chunks cuts a third of the tensor-pipe time per stage.
+constexpr uint32_t MMA_N1 = 136u, MMA_N2 = 72u;
 constexpr int N_EPI = 4, N_SOLVE = 16, N_PROD = 7;
 constexpr int NGB = N_SOLVE;                      // one packed system / L buffer per solver warp
 constexpr int W_EPI0 = 0, W_SOLVE0 = 4, W_MMA = 20, W_PROD0 = 21;
@@ -115,8 +119,8 @@ __device__ __forceinline__ void tma_gather4_pair(uint32_t dst_hi, uint32_t dst_l
 //   a_hi/lo : descriptors of the hi / lo chunks as A operand (M = 64)
 //   b3      : descriptor hi|lo|R  (three chunks, leading-dim offset one chunk)
 //   b2      : descriptor hi|R'    (two chunks, leading-dim offset three chunks)
-__device__ __forceinline__ void tc_stage_mma(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b3, uint64_t b2, uint32_t idesc192,
-                                             uint32_t idesc128, uint32_t accumulate, uint32_t bar_empty, uint32_t bar_acc, uint32_t last) {
+__device__ __forceinline__ void tc_stage_mma(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b3, uint64_t b2, uint32_t idesc_n1,
+                                             uint32_t idesc_n2, uint32_t accumulate, uint32_t bar_empty, uint32_t bar_acc, uint32_t last) {
     asm volatile(
         "{\n"
         ".reg .pred pe, pa, pl, pt;\n"
@@ -132,7 +136,7 @@ __device__ __forceinline__ void tc_stage_mma(uint32_t d, uint64_t a_hi, uint64_t
         "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
         "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n"
         "}\n" ::"r"(d),
-        "l"(a_hi), "l"(a_lo), "l"(b3), "r"(idesc192), "r"(idesc128), "r"(accumulate), "r"(bar_empty), "r"(bar_acc), "r"(last), "l"(b2)
+        "l"(a_hi), "l"(a_lo), "l"(b3), "r"(idesc_n1), "r"(idesc_n2), "r"(accumulate), "r"(bar_empty), "r"(bar_acc), "r"(last), "l"(b2)
         : "memory");
 }
 
@@ -462,20 +466,20 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
       } else {
         // ================================================================== MMA issuer
         uint32_t stage_ctr = 0, job = 0;
-        const uint32_t id192 = make_idesc(192), id128 = make_idesc(128);
+        const uint32_t idesc1 = make_idesc(MMA_N1), idesc2 = make_idesc(MMA_N2);
         for (int64_t row = first; row < last; ++row, ++job) {
             const int nst = stage_ptr[row + 1] - stage_ptr[row];
             const int acc = job % NACC;
             mbar_wait(bar_acc_empty(acc), ((job / NACC) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t d = tmem_base + (uint32_t)acc * 256u;
+            const uint32_t d = tmem_base + (uint32_t)acc * ACC_COLS;
             for (int st = 0; st < nst; ++st, ++stage_ctr) {
                 const int slot = stage_ctr % NSTG;
                 mbar_wait(bar_full(slot), (stage_ctr / NSTG) & 1);
                 tc_fence_after();
                 const uint32_t hi_a = sm_base + Smem::ring + slot * STAGE_BYTES;
                 tc_stage_mma(d, make_desc(hi_a, TILE_BYTES), make_desc(hi_a + TILE_BYTES, TILE_BYTES), make_desc(hi_a, TILE_BYTES),
-                             make_desc(hi_a, 3 * TILE_BYTES), id192, id128, st > 0 ? 1u : 0u, bar_empty(slot), bar_acc_full(acc),
+                             make_desc(hi_a, 3 * TILE_BYTES), idesc1, idesc2, st > 0 ? 1u : 0u, bar_empty(slot), bar_acc_full(acc),
                              st == nst - 1 ? 1u : 0u);
             }
         }
@@ -494,7 +498,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             float *bo = reinterpret_cast<float *>(sm + Smem::bsol + g * D * 4);
             float *G = reinterpret_cast<float *>(sm + Smem::gbuf + g * PK_FLOATS * 4);
             const int my_row = 16 * q + lane;                     // valid for lane < 16
-            const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * 256u;
+            const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * ACC_COLS;
 #pragma unroll
             for (int c0 = 0; c0 < D; c0 += 32) {
                 if (c0 > 16 * q + 15) break;                       // this quadrant's rows have no lower-triangle entry there
