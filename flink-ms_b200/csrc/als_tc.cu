@@ -36,8 +36,8 @@ namespace tc {
 constexpr int D = 64;
 constexpr int KROWS = 16;                         // ratings per stage == K of one tcgen05.mma (fp16)
 constexpr int TILE_BYTES = KROWS * 128;           // one 64-wide operand chunk of one stage (two swizzle atoms)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // hi | lo | R | R'
-constexpr int NSTG = 10;                          // ring depth (80 KB, 40 KB of gathers in flight)
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;       // hi | lo | R (R' lives in the same chunk tile as R, one 16-byte column group over)
+constexpr int NSTG = 13;                          // ring depth (78 KB, 52 KB of gathers in flight)
 constexpr int NACC = 2;                           // TMEM accumulator slots
 constexpr uint32_t ACC_COLS = 256u;               // TMEM columns per slot (136 used)
 // MMA widths: the first covers hi | lo | 8 rating columns, the second hi | 8 rating columns.  Only two rating columns
@@ -48,6 +48,8 @@ constexpr int NGB = N_SOLVE;                      // one packed system / L buffe
 constexpr int W_EPI0 = 0, W_SOLVE0 = 4, W_MMA = 20, W_PROD0 = 21;
 constexpr int NWARPS = 28;                        // 7 warpgroups: epilogue | 4 x solvers | MMA + producers x 2
 constexpr int REGS_EPI = 88, REGS_SOLVE = 80, REGS_AUX = 40;    // setmaxnreg budgets; sum <= launch allocation (72 x 896)
+// gather planes: one 256-byte row per factor row, hi halves then lo halves (one DRAM page burst serves both gathers)
+constexpr int PLANE_PITCH = 2 * D;
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 
 // Packed lower-triangular column-major storage of a 64x64 system (and later of its Cholesky factor): column c holds
@@ -80,6 +82,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes instead of spinning
+// (tight test_wait polling on the ring barriers measured slower: the polls compete with the barrier updates)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
@@ -94,6 +97,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// non-blocking probe of a phase (about 80 cycles of latency that can sit under other work)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -101,42 +118,46 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // TMA gather4: four rows (row indices r0..r3, 64 halves each) of a 2-D fp16 tensor -> 512 contiguous swizzled bytes.
 // Issues the hi-plane and lo-plane gathers of one row quartet from ONE elected lane (the operands must be valid in
 // every lane: they come from warp shuffles), predicated instead of branched so the compiler emits no lane loop.
-__device__ __forceinline__ void tma_gather4_pair(uint32_t dst_hi, uint32_t dst_lo, const CUtensorMap *map_hi, const CUtensorMap *map_lo,
-                                                 uint32_t bar, int r0, int r1, int r2, int r3) {
+__device__ __forceinline__ void tma_gather4_pair(uint32_t dst_hi, uint32_t dst_lo, const CUtensorMap *map, uint32_t bar, int r0, int r1,
+                                                 int r2, int r3) {
     asm volatile(
         "{\n"
         ".reg .pred pe;\n"
         "elect.sync _|pe, 0xffffffff;\n"
-        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%2, {%5, %6, %7, %8, %9}], [%4];\n"
-        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%1], [%3, {%5, %6, %7, %8, %9}], [%4];\n"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%2, {%4, %6, %7, %8, %9}], [%3];\n"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%1], [%2, {%5, %6, %7, %8, %9}], [%3];\n"
         "}\n" ::"r"(dst_hi),
-        "r"(dst_lo), "l"(map_hi), "l"(map_lo), "r"(bar), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        "r"(dst_lo), "l"(map), "r"(bar), "r"(0), "r"(D), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
         : "memory");
 }
 
 // One stage worth of tensor-core work, issued by one elected lane without a divergent branch.
-//   d       : TMEM address of the accumulator slot (column 0)
-//   a_hi/lo : descriptors of the hi / lo chunks as A operand (M = 64)
-//   b3      : descriptor hi|lo|R  (three chunks, leading-dim offset one chunk)
-//   b2      : descriptor hi|R'    (two chunks, leading-dim offset three chunks)
-__device__ __forceinline__ void tc_stage_mma(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b3, uint64_t b2, uint32_t idesc_n1,
-                                             uint32_t idesc_n2, uint32_t accumulate, uint32_t bar_empty, uint32_t bar_acc, uint32_t last) {
+//   d        : TMEM address of the accumulator slot (column 0)
+//   lo_*     : low words of the shared-memory descriptors (start address and leading-dim offset; the high word is
+//              the same for all): hi chunk as A (also hi|lo|R as B: the same bits), lo chunk as A, hi|R' as B
+__device__ __forceinline__ void tc_stage_mma(uint32_t d, uint32_t lo_hi, uint32_t lo_lo, uint32_t lo_b2, uint32_t idesc_n1, uint32_t idesc_n2,
+                                             uint32_t accumulate, uint32_t bar_empty, uint32_t bar_acc, uint32_t last) {
+    constexpr uint32_t DESC_HI = (uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
     asm volatile(
         "{\n"
         ".reg .pred pe, pa, pl, pt;\n"
         ".reg .b32 d2;\n"
+        ".reg .b64 ahi, alo, b2;\n"
         "elect.sync _|pe, 0xffffffff;\n"
         "setp.ne.b32 pa, %6, 0;\n"
         "setp.ne.b32 pt, %9, 0;\n"
         "and.pred pl, pt, pe;\n"
         "setp.eq.u32 pt, %0, %0;\n"
         "add.u32 d2, %0, 64;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %4, pa;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [d2], %2, %10, %5, pt;\n"
+        "mov.b64 ahi, {%1, %10};\n"
+        "mov.b64 alo, {%2, %10};\n"
+        "mov.b64 b2, {%3, %10};\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ahi, ahi, %4, pa;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [d2], alo, b2, %5, pt;\n"
         "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
         "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n"
         "}\n" ::"r"(d),
-        "l"(a_hi), "l"(a_lo), "l"(b3), "r"(idesc_n1), "r"(idesc_n2), "r"(accumulate), "r"(bar_empty), "r"(bar_acc), "r"(last), "l"(b2)
+        "r"(lo_hi), "r"(lo_lo), "r"(lo_b2), "r"(idesc_n1), "r"(idesc_n2), "r"(accumulate), "r"(bar_empty), "r"(bar_acc), "r"(last), "r"(DESC_HI)
         : "memory");
 }
 
@@ -378,9 +399,9 @@ __device__ __forceinline__ void solver_trsm_syrk(float2 (&A)[16], float &b1, flo
 
 template <bool DUMP>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
-    const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const int64_t *__restrict__ ptr,
+    const __grid_constant__ CUtensorMap map_pl, const int64_t *__restrict__ ptr,
     const int32_t *__restrict__ stage_ptr, const int32_t *__restrict__ colp, const float *__restrict__ valp,
-    const int32_t *__restrict__ cta_rows, float *__restrict__ T, __half *__restrict__ T_hi, __half *__restrict__ T_lo, float lambda,
+    const int32_t *__restrict__ cta_rows, float *__restrict__ T, __half *__restrict__ T_pl, float lambda,
     int64_t row_begin, int *__restrict__ info, float *__restrict__ dump) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
@@ -450,7 +471,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
                 const uint32_t w0 = (uint32_t)__half_as_ushort(rh) | ((uint32_t)__half_as_ushort(rl) << 16);
                 const uint32_t w1 = (uint32_t)__half_as_ushort(rh) << 16;
                 *reinterpret_cast<uint32_t *>(sm + Smem::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + off) = w0;
-                *reinterpret_cast<uint32_t *>(sm + Smem::ring + slot * STAGE_BYTES + 3 * TILE_BYTES + off) = w1;
+                *reinterpret_cast<uint32_t *>(sm + Smem::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + (off ^ 16u)) = w1;   // logical column group 1
             }
             fence_proxy_async();
             __syncwarp();
@@ -458,30 +479,40 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             __syncwarp();
 #pragma unroll
             for (int t = 0; t < 4; ++t)
-                tma_gather4_pair(stage + t * 512, stage + TILE_BYTES + t * 512, &map_hi, &map_lo, bar_full(slot), r[4 * t], r[4 * t + 1],
+                tma_gather4_pair(stage + t * 512, stage + TILE_BYTES + t * 512, &map_pl, bar_full(slot), r[4 * t], r[4 * t + 1],
                                  r[4 * t + 2], r[4 * t + 3]);
             idx0 = idx1; rt0 = rt1;
             idx1 = idx2; rt1 = rt2;
         }
       } else {
         // ================================================================== MMA issuer
-        uint32_t stage_ctr = 0, job = 0;
+        // One warp, in-order, is the pacing agent of a gather-bound half-step (measured: ~290 cycles per stage when every
+        // stage paid a blocking try_wait (~80 cycles even when the data is there), four descriptor builds and a modulo).
+        // So the ring cursor (slot, phase, descriptor words, barrier addresses) advances incrementally and the probe
+        // of the NEXT slot's full barrier is issued before this stage's MMAs, hiding its latency under them.
+        uint32_t job = 0;
         const uint32_t idesc1 = make_idesc(MMA_N1), idesc2 = make_idesc(MMA_N2);
+        constexpr uint32_t LBO_T = (uint32_t)(TILE_BYTES >> 4) << 16, LBO_B2 = (uint32_t)((2 * TILE_BYTES + 16) >> 4) << 16;
+        const uint32_t enc0 = ((sm_base + Smem::ring) >> 4) & 0x3FFF;
+        uint32_t slot = 0, ph = 0, enc = enc0, ready = 0;
+        int nst = (first < last) ? stage_ptr[first + 1] - stage_ptr[first] : 0;
         for (int64_t row = first; row < last; ++row, ++job) {
-            const int nst = stage_ptr[row + 1] - stage_ptr[row];
+            const int nst_next = (row + 1 < last) ? stage_ptr[row + 2] - stage_ptr[row + 1] : 0;
             const int acc = job % NACC;
             mbar_wait(bar_acc_empty(acc), ((job / NACC) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d = tmem_base + (uint32_t)acc * ACC_COLS;
-            for (int st = 0; st < nst; ++st, ++stage_ctr) {
-                const int slot = stage_ctr % NSTG;
-                mbar_wait(bar_full(slot), (stage_ctr / NSTG) & 1);
+            for (int st = 0; st < nst; ++st) {
+                if (!ready) mbar_wait(bar0 + 8u * slot, ph);
                 tc_fence_after();
-                const uint32_t hi_a = sm_base + Smem::ring + slot * STAGE_BYTES;
-                tc_stage_mma(d, make_desc(hi_a, TILE_BYTES), make_desc(hi_a + TILE_BYTES, TILE_BYTES), make_desc(hi_a, TILE_BYTES),
-                             make_desc(hi_a, 3 * TILE_BYTES), idesc1, idesc2, st > 0 ? 1u : 0u, bar_empty(slot), bar_acc_full(acc),
-                             st == nst - 1 ? 1u : 0u);
+                uint32_t nslot = slot + 1, nph = ph, nenc = enc + (STAGE_BYTES >> 4);
+                if (nslot == NSTG) { nslot = 0; nph ^= 1u; nenc = enc0; }
+                const uint32_t nready = mbar_test(bar0 + 8u * nslot, nph);
+                tc_stage_mma(d, enc | LBO_T, (enc + (TILE_BYTES >> 4)) | LBO_T, enc | LBO_B2, idesc1, idesc2, st > 0 ? 1u : 0u,
+                             bar0 + 8u * (NSTG + slot), bar_acc_full(acc), st == nst - 1 ? 1u : 0u);
+                slot = nslot; ph = nph; enc = nenc; ready = nready;
             }
+            nst = nst_next;
         }
       }
     } else if (warp < W_SOLVE0) {
@@ -603,8 +634,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             __half h0, l0, h1, l1;
             split_half(b0, h0, l0);
             split_half(b1, h1, l1);
-            T_hi[row * D + lane] = h0; T_hi[row * D + lane + 32] = h1;
-            T_lo[row * D + lane] = l0; T_lo[row * D + lane + 32] = l1;
+            __half *tp = T_pl + row * PLANE_PITCH + lane;
+            tp[0] = h0; tp[32] = h1;
+            tp[D] = l0; tp[D + 32] = l1;
             const bool bad = !(fabsf(b0) <= 3.0e38f) || !(fabsf(b1) <= 3.0e38f);                 // NaN / inf: the factorisation broke down
             if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(info, 1);
         }
@@ -617,13 +649,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
 }
 
 // fp32 factor rows -> gather planes (after init, after an all-gather, after the generic kernel wrote a side)
-__global__ void k_split_planes(const float *__restrict__ f, int64_t n, __half *__restrict__ hi, __half *__restrict__ lo) {
+__global__ void k_split_planes(const float *__restrict__ f, int64_t n, __half *__restrict__ pl) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     __half h, l;
     split_half(f[i], h, l);
-    hi[i] = h;
-    lo[i] = l;
+    const int64_t o = (i / D) * PLANE_PITCH + (i % D);
+    pl[o] = h;
+    pl[o + D] = l;
 }
 
 // ---- stage CSR build (one-off per load / shard geometry)
@@ -708,7 +741,7 @@ int als_tc_refresh_planes(fms_ctx *ctx, int s) {
     const int64_t n = (A.shard_rows[s] * A.shard_count) * tc::D;
     if (n > 0) {
         __half *hi = reinterpret_cast<__half *>(A.plane[s].p);
-        tc::k_split_planes<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(A.fac[s].p, n, hi, hi + (int64_t)plane_rows(A, s) * tc::D);
+        tc::k_split_planes<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(A.fac[s].p, n, hi);
         FMS_LAUNCH_CHECK(ctx);
     }
     A.plane_valid[s] = true;
@@ -716,8 +749,8 @@ int als_tc_refresh_planes(fms_ctx *ctx, int s) {
 }
 
 static int make_map(fms_ctx *ctx, CUtensorMap *m, void *base, int64_t rows) {
-    const cuuint64_t gdim[2] = {(cuuint64_t)tc::D, (cuuint64_t)rows};
-    const cuuint64_t gstr[1] = {(cuuint64_t)tc::D * 2};
+    const cuuint64_t gdim[2] = {(cuuint64_t)tc::PLANE_PITCH, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)tc::PLANE_PITCH * 2};
     const cuuint32_t box[2] = {(cuuint32_t)tc::D, 1};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = get_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -774,11 +807,10 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
     FMS_TRY(ensure_planes(ctx, which));
     FMS_TRY(ensure_planes(ctx, partner));
     if (!A.plane_valid[partner]) FMS_TRY(als_tc_refresh_planes(ctx, partner));
-    const int64_t prow = plane_rows(A, partner), trow = plane_rows(A, which);
+    const int64_t prow = plane_rows(A, partner);
     __half *p_hi = reinterpret_cast<__half *>(A.plane[partner].p), *t_hi = reinterpret_cast<__half *>(A.plane[which].p);
-    CUtensorMap m_hi, m_lo;
-    FMS_TRY(make_map(ctx, &m_hi, p_hi, prow));
-    FMS_TRY(make_map(ctx, &m_lo, p_hi + prow * tc::D, prow));
+    CUtensorMap m_pl;
+    FMS_TRY(make_map(ctx, &m_pl, p_hi, prow));
     const int zero_row = (int)(A.shard_rows[partner] * A.shard_count);
     const size_t smem = (size_t)tc::Smem::total + 1024;
     const int64_t rows = re - rb;
@@ -786,15 +818,15 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
     FMS_TRY(ensure_stage_csr(ctx, which, rb, re, zero_row, grid));
     if (dump) {
         FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::k_als_rows_tc64<true><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_hi, m_lo, A.ptr[which].p, A.stage_ptr[which].p,
+        tc::k_als_rows_tc64<true><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_pl, A.ptr[which].p, A.stage_ptr[which].p,
                                                                                  A.colp[which].p, A.valp[which].p, A.cta_rows[which].p,
-                                                                                 A.fac[which].p, t_hi, t_hi + trow * tc::D, lambda, rb,
+                                                                                 A.fac[which].p, t_hi, lambda, rb,
                                                                                  A.info.p, dump);
     } else {
         FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::k_als_rows_tc64<false><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_hi, m_lo, A.ptr[which].p, A.stage_ptr[which].p,
+        tc::k_als_rows_tc64<false><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_pl, A.ptr[which].p, A.stage_ptr[which].p,
                                                                                   A.colp[which].p, A.valp[which].p, A.cta_rows[which].p,
-                                                                                  A.fac[which].p, t_hi, t_hi + trow * tc::D, lambda, rb,
+                                                                                  A.fac[which].p, t_hi, lambda, rb,
                                                                                   A.info.p, nullptr);
     }
     FMS_LAUNCH_CHECK(ctx);
@@ -813,7 +845,7 @@ int als_tc_planes(fms_ctx *ctx, int s, void **hi, void **lo, int64_t *rows_padde
     FMS_TRY(ensure_planes(ctx, s));
     __half *h = reinterpret_cast<__half *>(A.plane[s].p);
     if (hi) *hi = h;
-    if (lo) *lo = h + plane_rows(A, s) * tc::D;
+    if (lo) *lo = h + tc::D;                                   // interleaved: row pitch 2 * rank halves, lo half follows hi
     if (rows_padded) *rows_padded = A.shard_rows[s] * A.shard_count;
     return FMS_OK;
 }

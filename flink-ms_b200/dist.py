@@ -56,13 +56,13 @@ class ContextALSBackend:
         self.ctx.als_factors_updated(which)
 
     def plane_tensors(self, which, rank):
-        """(hi, lo) fp16 views of the gather planes, or None when the tensor-core path does not cover `rank`."""
+        """fp16 views of the gather planes as a tuple of tensors to all-gather, or None when the tensor-core path does
+        not cover `rank`.  The planes are interleaved (one row = rank hi halves then rank lo halves), i.e. ONE tensor."""
         try:
-            hi, lo, rows = self.ctx.als_planes_device(which)
+            hi, _lo, rows = self.ctx.als_planes_device(which)
         except Exception:  # noqa: BLE001  (FMS_ERR_UNSUPPORTED: generic kernel in use)
             return None
-        return (device_view(hi, rows * rank, torch.float16, self.device).view(rows, rank),
-                device_view(lo, rows * rank, torch.float16, self.device).view(rows, rank))
+        return (device_view(hi, rows * 2 * rank, torch.float16, self.device).view(rows, 2 * rank),)
 
     def planes_updated(self, which):
         self.ctx.als_planes_updated(which)
@@ -96,8 +96,8 @@ class DistributedALS:
             return
         planes = self.b.plane_tensors(which, self.rank_dim) if hasattr(self.b, "plane_tensors") else None
         if planes is not None:
-            self._gather(planes[0])
-            self._gather(planes[1])
+            for t in planes:
+                self._gather(t)
             self.b.planes_updated(which)
             self._stale.add(which)
         else:

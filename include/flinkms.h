@@ -111,10 +111,12 @@ FMS_API int fms_als_factors_device(fms_ctx *ctx, int which, void **dev_ptr, int6
 /* Tell the library a factor matrix was rewritten from outside (after an all-gather) so derived device
  * state (split-precision gather planes of the tensor-core kernel) is refreshed. */
 FMS_API int fms_als_factors_updated(fms_ctx *ctx, int which);
-/* Tensor-core path (rank 64): device views of the two fp16 gather planes of a side (rows_padded rows of 64 halves
- * each, same shard layout as the factor matrix).  A sharded host may all-gather the PLANES between half-steps
- * instead of the fp32 matrix (same bytes, no re-split afterwards) and call fms_als_planes_updated; it must then
- * all-gather the fp32 matrix once before reading factors out. */
+/* Tensor-core path (rank 64): device view of the fp16 split-precision gather planes of a side.  The planes are
+ * interleaved: rows_padded rows of 2 * rank halves, the `rank` hi halves of a factor row followed by its `rank` lo
+ * halves (one 256-byte burst per gathered row); *hi is the base, *lo = *hi + rank halves, shard layout as for the
+ * factor matrix.  A sharded host may all-gather the PLANES ([rows_padded, 2 * rank] fp16, one tensor) between
+ * half-steps instead of the fp32 matrix (same bytes, no re-split afterwards) and call fms_als_planes_updated; it
+ * must then all-gather the fp32 matrix once before reading factors out. */
 FMS_API int fms_als_planes_device(fms_ctx *ctx, int which, void **hi, void **lo, int64_t *rows_padded);
 FMS_API int fms_als_planes_updated(fms_ctx *ctx, int which);
 /* number of rows whose Cholesky hit a non-positive pivot in the last half-step (dposv info != 0; FlinkML
