@@ -311,16 +311,21 @@ def main():
     if rank == 0 and world == 1:
         rng = np.random.default_rng(7)
         nq = 1_000_000
-        qu = rng.integers(0, args.users, nq, dtype=np.int64)
-        qi = rng.integers(0, args.items, nq, dtype=np.int64)
-        ctx.als_predict(qu[:1000], qi[:1000])                                        # warm-up (fp64 model copy)
+        # query and result buffers in pinned host memory (a JVM host's direct ByteBuffers)
+        qu = torch.empty(nq, dtype=torch.int64, pin_memory=True).numpy()
+        qi = torch.empty(nq, dtype=torch.int64, pin_memory=True).numpy()
+        qu[:] = rng.integers(0, args.users, nq, dtype=np.int64)
+        qi[:] = rng.integers(0, args.items, nq, dtype=np.int64)
+        p_out = torch.empty(nq, dtype=torch.float64, pin_memory=True).numpy()
+        p_found = torch.empty(nq, dtype=torch.uint8, pin_memory=True).numpy()
+        ctx.als_predict(qu, qi, p_out, p_found)                                      # warm-up (fp64 model copy, scratch)
         t0 = time.perf_counter()
-        for _ in range(3):
-            out, found = ctx.als_predict(qu, qi)
-        dtp = (time.perf_counter() - t0) / 3
+        for _ in range(5):
+            out, found = ctx.als_predict(qu, qi, p_out, p_found)
+        dtp = (time.perf_counter() - t0) / 5
         predict = {"metric": "als_lookups_per_sec", "value": nq / dtp, "unit": "lookups/s", "batch": nq,
                    "found_fraction": float(found.mean()),
-                   "note": "fms_als_predict through the C-ABI: host ids in, H2D, id lookup + fp64 dot on device, D2H"}
+                   "note": "fms_als_predict through the C-ABI: pinned host ids in, H2D, id lookup + fp64 dot on device, D2H into pinned host buffers"}
 
     # ---------------------------------------------------------------------------------------- CPU baseline (rank 0, N=1)
     cpu = None

@@ -220,14 +220,21 @@ class Context:
                                                 _p(itf, _f64p), len(ii), rank))
         self._als_shape = (len(ui), len(ii), rank)
 
-    def als_predict(self, u, i):
+    def als_predict(self, u, i, out=None, found=None):
+        """Batched lookup-and-dot.  `out` (float64) / `found` (uint8) may be caller-owned buffers, e.g. pinned host memory
+        (what a JVM host passes as a direct ByteBuffer); they are then returned as is (found as uint8)."""
         u, i = _i64(u), _i64(i)
         if len(u) != len(i):
             raise ValueError("u/i lengths differ")
-        out = np.empty(len(u), np.float64)
-        found = np.empty(len(u), np.uint8)
+        own = found is None
+        if out is None:
+            out = np.empty(len(u), np.float64)
+        if found is None:
+            found = np.empty(len(u), np.uint8)
+        if out.dtype != np.float64 or found.dtype != np.uint8 or len(out) < len(u) or len(found) < len(u):
+            raise ValueError("out must be float64 and found uint8, both at least len(u) long")
         self._check(self._lib.fms_als_predict(self._h, _p(u, _i64p), _p(i, _i64p), len(u), _p(out, _f64p), _p(found, _u8p)))
-        return out, found.astype(bool)
+        return out, (found.astype(bool) if own else found)
 
     def als_mse(self, u, i, rating):
         u, i, r = _i64(u), _i64(i), _f64(rating)

@@ -137,7 +137,8 @@ __device__ __forceinline__ void tma_gather4_pair(uint32_t dst_hi, uint32_t dst_l
 //              the same for all): hi chunk as A (also hi|lo|R as B: the same bits), lo chunk as A, hi|R' as B
 __device__ __forceinline__ void tc_stage_mma(uint32_t d, uint32_t lo_hi, uint32_t lo_lo, uint32_t lo_b2, uint32_t idesc_n1, uint32_t idesc_n2,
                                              uint32_t accumulate, uint32_t bar_empty, uint32_t bar_acc, uint32_t last) {
-    constexpr uint32_t DESC_HI = (uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+    // descriptor high word 0x40004040: SBO 1024 B (bits 32-45), version 1 (bit 46), SWIZZLE_128B (bits 61-63)
+    static_assert(((uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29)) == 0x40004040u, "descriptor high word");
     asm volatile(
         "{\n"
         ".reg .pred pe, pa, pl, pt;\n"
@@ -149,15 +150,15 @@ __device__ __forceinline__ void tc_stage_mma(uint32_t d, uint32_t lo_hi, uint32_
         "and.pred pl, pt, pe;\n"
         "setp.eq.u32 pt, %0, %0;\n"
         "add.u32 d2, %0, 64;\n"
-        "mov.b64 ahi, {%1, %10};\n"
-        "mov.b64 alo, {%2, %10};\n"
-        "mov.b64 b2, {%3, %10};\n"
+        "mov.b64 ahi, {%1, 0x40004040};\n"
+        "mov.b64 alo, {%2, 0x40004040};\n"
+        "mov.b64 b2, {%3, 0x40004040};\n"
         "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ahi, ahi, %4, pa;\n"
         "@pe tcgen05.mma.cta_group::1.kind::f16 [d2], alo, b2, %5, pt;\n"
         "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
         "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n"
         "}\n" ::"r"(d),
-        "r"(lo_hi), "r"(lo_lo), "r"(lo_b2), "r"(idesc_n1), "r"(idesc_n2), "r"(accumulate), "r"(bar_empty), "r"(bar_acc), "r"(last), "r"(DESC_HI)
+        "r"(lo_hi), "r"(lo_lo), "r"(lo_b2), "r"(idesc_n1), "r"(idesc_n2), "r"(accumulate), "r"(bar_empty), "r"(bar_acc), "r"(last)
         : "memory");
 }
 

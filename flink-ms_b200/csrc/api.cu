@@ -291,9 +291,9 @@ static int predict_common(fms_ctx *ctx, const int64_t *u, const int64_t *i, int6
 FMS_API int fms_als_predict(fms_ctx *ctx, const int64_t *u, const int64_t *i, int64_t n, double *out, uint8_t *found) {
     CHECK_CTX(ctx);
     if (n && !out) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_predict: out is null");
-    DevBuf<int64_t> du, di;
-    DevBuf<double> dout;
-    DevBuf<uint8_t> dfound;
+    DevBuf<int64_t> &du = ctx->als.q_u, &di = ctx->als.q_i;
+    DevBuf<double> &dout = ctx->als.q_out;
+    DevBuf<uint8_t> &dfound = ctx->als.q_found;
     FMS_TRY(predict_common(ctx, u, i, n, du, di, dout, dfound));
     if (n) {
         FMS_CUDA(ctx, cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -307,9 +307,10 @@ FMS_API int fms_als_mse(fms_ctx *ctx, const int64_t *u, const int64_t *i, const 
                         int64_t *n_used) {
     CHECK_CTX(ctx);
     if (n && !rating) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_mse: rating is null");
-    DevBuf<int64_t> du, di;
-    DevBuf<double> dout, dr, acc;
-    DevBuf<uint8_t> dfound;
+    DevBuf<int64_t> &du = ctx->als.q_u, &di = ctx->als.q_i;
+    DevBuf<double> &dout = ctx->als.q_out, &dr = ctx->als.q_rating;
+    DevBuf<double> acc;
+    DevBuf<uint8_t> &dfound = ctx->als.q_found;
     FMS_TRY(predict_common(ctx, u, i, n, du, di, dout, dfound));
     FMS_CUDA(ctx, dr.alloc((size_t)n));
     FMS_CUDA(ctx, acc.alloc(2));

@@ -51,6 +51,10 @@ struct AlsState {
     int rank = 0;
     int kernel = FMS_ALS_KERNEL_AUTO;
     DevBuf<int64_t> ids[2];                  // sorted distinct ids (createBlockInformation)
+    // serving scratch (grow-only): query ids, results, found flags -- a lookup batch must not pay cudaMalloc / cudaFree
+    DevBuf<int64_t> q_u, q_i;
+    DevBuf<double> q_out, q_rating;
+    DevBuf<uint8_t> q_found;
     DevBuf<int64_t> ptr[2];                  // CSR row pointers  (side 0: by user, side 1: by item)
     DevBuf<int32_t> col[2];                  // dense partner index, ascending inside a row
     DevBuf<float> val[2];                    // rating
