@@ -154,7 +154,9 @@ def run_reference(args, rank, world):
 def workload_config(args, world):
     return {"workload": f"ALS rank={args.rank}, {args.users} users x {args.items} items, {args.nnz} synthetic ratings "
                         f"(BASELINE.json configs[1]); lambda=0.9 seed=42; step = 1 ALS iteration (2 half-steps)",
-            "parallelism": f"rows sharded over {world} GPU(s), NCCL all-gather of factor shards" if world > 1 else "1 GPU",
+            "parallelism": (f"rows sharded over {world} GPU(s); "
+                            + ("solver warps store each new gather-plane row into every replica over NVLink (CUDA IPC), barrier per half-step"
+                               if getattr(args, "als_p2p", 1) else "NCCL all-gather of the gather-plane shards")) if world > 1 else "1 GPU",
             "l2": "inputs larger than L2 (CSR pair 1.6 GB + factors 0.28 GB per iteration vs 126 MB L2); no flush needed"}
 
 
@@ -179,6 +181,8 @@ def main():
     ap.add_argument("--cpu-nnz", type=int, default=10_000_000)
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--als-kernel", type=int, default=0)
+    ap.add_argument("--als-chunks", type=int, default=4, help="N>1, without --als-p2p 1: solve each shard in this many chunks, all-gather overlapped")
+    ap.add_argument("--als-p2p", type=int, default=1, help="N>1: the kernel stores plane rows into all replicas over NVLink (CUDA IPC)")
     ap.add_argument("--svm-kernel", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -238,7 +242,9 @@ def main():
     ctx.als_init(d, 42)
     ctx.synchronize()
     log(f"[rank {rank}] load+index {time.perf_counter() - t0:.2f}s: {n_users} users, {n_items} items")
-    dals = D.DistributedALS(D.ContextALSBackend(ctx, dev), d)
+    backend = D.ContextALSBackend(ctx, dev)
+    p2p = bool(world > 1 and args.als_p2p and backend.enable_p2p())
+    dals = D.DistributedALS(backend, d, max_chunks=args.als_chunks)
 
     for _ in range(args.warmup):
         dals.iteration(0.9)
@@ -294,7 +300,10 @@ def main():
         else:
             ctx.als_load(h_u.numpy(), h_i.numpy(), h_r.numpy(), rank, world)
             ctx.als_init(d, 42)
-            D.DistributedALS(D.ContextALSBackend(ctx, dev), d).fit(T, 0.9)
+            be2 = D.ContextALSBackend(ctx, dev)
+            if args.als_p2p:
+                be2.enable_p2p()                                                          # part of the timed call: IPC handle exchange
+            D.DistributedALS(be2, d, max_chunks=args.als_chunks).fit(T, 0.9)
         ids_u, F_u = ctx.als_get_factors(N.USERS, o_uid, o_U)                             # D2H of the result
         ids_i, F_i = ctx.als_get_factors(N.ITEMS, o_iid, o_I)
         barrier()

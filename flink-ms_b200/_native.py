@@ -44,9 +44,12 @@ SIGNATURES = {
     "fms_als_load": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64, C.c_int, C.c_int, _i64p, _i64p]),
     "fms_als_init": (C.c_int, [_vp, C.c_int, C.c_int64]),
     "fms_als_half_step": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "fms_als_half_step_chunk": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int, C.c_int]),
     "fms_als_factors_device": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), _i64p, _i64p, _i64p]),
     "fms_als_factors_updated": (C.c_int, [_vp, C.c_int]),
     "fms_als_planes_device": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _i64p]),
+    "fms_als_planes_ipc_handle": (C.c_int, [_vp, C.c_int, _vp]),
+    "fms_als_planes_open_peers": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
     "fms_als_planes_updated": (C.c_int, [_vp, C.c_int]),
     "fms_als_last_info": (C.c_int, [_vp, _i64p]),
     "fms_als_set_kernel": (C.c_int, [_vp, C.c_int]),
@@ -176,6 +179,9 @@ class Context:
     def als_half_step(self, which, lam):
         self._check(self._lib.fms_als_half_step(self._h, which, lam))
 
+    def als_half_step_chunk(self, which, lam, chunk, n_chunks):
+        self._check(self._lib.fms_als_half_step_chunk(self._h, which, lam, chunk, n_chunks))
+
     def als_set_kernel(self, kernel):
         self._check(self._lib.fms_als_set_kernel(self._h, kernel))
 
@@ -193,6 +199,14 @@ class Context:
         hi, lo, rows = _vp(), _vp(), C.c_int64()
         self._check(self._lib.fms_als_planes_device(self._h, which, C.byref(hi), C.byref(lo), C.byref(rows)))
         return int(hi.value or 0), int(lo.value or 0), rows.value
+
+    def als_planes_ipc_handle(self, which) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.fms_als_planes_ipc_handle(self._h, which, buf))
+        return buf.raw
+
+    def als_planes_open_peers(self, which, handles: bytes, n: int):
+        self._check(self._lib.fms_als_planes_open_peers(self._h, which, C.c_char_p(handles) if n else None, n))
 
     def als_planes_updated(self, which):
         self._check(self._lib.fms_als_planes_updated(self._h, which))

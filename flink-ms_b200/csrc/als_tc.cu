@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
     const __grid_constant__ CUtensorMap map_pl, const int64_t *__restrict__ ptr,
     const int32_t *__restrict__ stage_ptr, const int32_t *__restrict__ colp, const float *__restrict__ valp,
     const int32_t *__restrict__ cta_rows, float *__restrict__ T, __half *__restrict__ T_pl, float lambda,
-    int64_t row_begin, int *__restrict__ info, float *__restrict__ dump) {
+    int64_t row_begin, int *__restrict__ info, float *__restrict__ dump, __half *const *__restrict__ peers, int n_peers) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
     const uint32_t sm_base = smem_u32(sm);
@@ -635,9 +635,21 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             __half h0, l0, h1, l1;
             split_half(b0, h0, l0);
             split_half(b1, h1, l1);
-            __half *tp = T_pl + row * PLANE_PITCH + lane;
-            tp[0] = h0; tp[32] = h1;
-            tp[D] = l0; tp[D + 32] = l1;
+            // the plane row (256 B) is staged through this warp's scratch so that each lane stores 8 contiguous bytes --
+            // into the local plane, or, when peers are mapped, into every rank's replica (posted NVLink writes): the
+            // all-gather of the half-step happens while the other solver warps are still factorising
+            __half *stg = reinterpret_cast<__half *>(invd);
+            stg[lane] = h0; stg[lane + 32] = h1;
+            stg[D + lane] = l0; stg[D + 32 + lane] = l1;
+            __syncwarp();
+            const uint2 prow = reinterpret_cast<const uint2 *>(stg)[lane];
+            __syncwarp();
+            const int64_t poff = row * PLANE_PITCH + 4 * lane;
+            if (n_peers == 0) {
+                *reinterpret_cast<uint2 *>(T_pl + poff) = prow;
+            } else {
+                for (int p = 0; p < n_peers; ++p) *reinterpret_cast<uint2 *>(peers[p] + poff) = prow;
+            }
             const bool bad = !(fabsf(b0) <= 3.0e38f) || !(fabsf(b1) <= 3.0e38f);                 // NaN / inf: the factorisation broke down
             if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(info, 1);
         }
@@ -728,6 +740,7 @@ static int ensure_planes(fms_ctx *ctx, int s) {
     AlsState &A = ctx->als;
     const size_t need = (size_t)plane_rows(A, s) * tc::D * 2;
     if (A.plane[s].n < need || !A.plane[s].p || A.plane_rows[s] != plane_rows(A, s)) {
+        als_tc_close_peers(ctx, s);                              // exported handles / peer mappings die with the old buffer
         FMS_CUDA(ctx, A.plane[s].alloc(need));
         FMS_CUDA(ctx, cudaMemsetAsync(A.plane[s].p, 0, A.plane[s].n * sizeof(uint16_t), ctx->stream));
         A.plane_rows[s] = plane_rows(A, s);
@@ -813,6 +826,8 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
     CUtensorMap m_pl;
     FMS_TRY(make_map(ctx, &m_pl, p_hi, prow));
     const int zero_row = (int)(A.shard_rows[partner] * A.shard_count);
+    __half *const *peers = A.peer_n[which] > 0 ? reinterpret_cast<__half *const *>(A.peer_tab[which].p) : nullptr;
+    const int n_peers = A.peer_n[which];
     const size_t smem = (size_t)tc::Smem::total + 1024;
     const int64_t rows = re - rb;
     const int grid = (int)(rows < ctx->sm_count ? rows : ctx->sm_count);
@@ -822,13 +837,13 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
         tc::k_als_rows_tc64<true><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_pl, A.ptr[which].p, A.stage_ptr[which].p,
                                                                                  A.colp[which].p, A.valp[which].p, A.cta_rows[which].p,
                                                                                  A.fac[which].p, t_hi, lambda, rb,
-                                                                                 A.info.p, dump);
+                                                                                 A.info.p, dump, peers, n_peers);
     } else {
         FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc::k_als_rows_tc64<false><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_pl, A.ptr[which].p, A.stage_ptr[which].p,
                                                                                   A.colp[which].p, A.valp[which].p, A.cta_rows[which].p,
                                                                                   A.fac[which].p, t_hi, lambda, rb,
-                                                                                  A.info.p, nullptr);
+                                                                                  A.info.p, nullptr, peers, n_peers);
     }
     FMS_LAUNCH_CHECK(ctx);
     // the kernel wrote the planes of its own rows; with one shard that is the whole side
@@ -848,6 +863,54 @@ int als_tc_planes(fms_ctx *ctx, int s, void **hi, void **lo, int64_t *rows_padde
     if (hi) *hi = h;
     if (lo) *lo = h + tc::D;                                   // interleaved: row pitch 2 * rank halves, lo half follows hi
     if (rows_padded) *rows_padded = A.shard_rows[s] * A.shard_count;
+    return FMS_OK;
+}
+
+// ---- peer-to-peer plane exchange (one process per GPU on one node): CUDA IPC handles in, device table of replicas out
+void als_tc_close_peers(fms_ctx *ctx, int s) {
+    AlsState &A = ctx->als;
+    for (int r = 0; r < A.peer_n[s]; ++r) {
+        if (A.peer_open[s][r]) cudaIpcCloseMemHandle(A.peer_open[s][r]);
+        A.peer_open[s][r] = nullptr;
+    }
+    A.peer_n[s] = 0;
+}
+
+int als_tc_ipc_handle(fms_ctx *ctx, int s, void *handle64) {
+    AlsState &A = ctx->als;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    FMS_TRY(ensure_planes(ctx, s));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));                     // the zero fill of a fresh buffer is done
+    cudaIpcMemHandle_t h;
+    FMS_CUDA(ctx, cudaIpcGetMemHandle(&h, A.plane[s].p));
+    memcpy(handle64, &h, sizeof h);
+    return FMS_OK;
+}
+
+int als_tc_open_peers(fms_ctx *ctx, int s, const void *handles, int n) {
+    AlsState &A = ctx->als;
+    if (n != A.shard_count || n > 64) return fail(ctx, FMS_ERR_INVALID_ARG, "peer table: %d handles for %d shards", n, A.shard_count);
+    FMS_TRY(ensure_planes(ctx, s));
+    als_tc_close_peers(ctx, s);
+    unsigned long long tab[64];
+    for (int r = 0; r < n; ++r) {
+        if (r == A.shard_index) { tab[r] = (unsigned long long)(uintptr_t)A.plane[s].p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char *>(handles) + (size_t)r * sizeof h, sizeof h);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            A.peer_n[s] = r;                                               // close what was opened so far
+            als_tc_close_peers(ctx, s);
+            return fail(ctx, FMS_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        A.peer_open[s][r] = p;
+        tab[r] = (unsigned long long)(uintptr_t)p;
+    }
+    A.peer_n[s] = n;
+    FMS_CUDA(ctx, A.peer_tab[s].alloc(64));
+    FMS_CUDA(ctx, cudaMemcpyAsync(A.peer_tab[s].p, tab, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FMS_OK;
 }
 

@@ -72,8 +72,10 @@ FMS_API int fms_create(fms_ctx **out, const int *device_ids, int n_devices) {
 FMS_API void fms_destroy(fms_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    als_tc_close_peers(ctx, 0);
+    als_tc_close_peers(ctx, 1);
     if (ctx->stream) {
-        cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -131,15 +133,18 @@ FMS_API int fms_als_set_kernel(fms_ctx *ctx, int kernel) {
     return FMS_OK;
 }
 
-FMS_API int fms_als_half_step(fms_ctx *ctx, int which, double lambda) {
-    CHECK_CTX(ctx);
+static int als_half_step_rows(fms_ctx *ctx, int which, double lambda, int chunk, int n_chunks, const char *fn) {
     AlsState &A = ctx->als;
-    if (!A.loaded || !A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_half_step: load + init first");
-    if (which != FMS_USERS && which != FMS_ITEMS) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_half_step: which = %d", which);
+    if (!A.loaded || !A.inited) return fail(ctx, FMS_ERR_STATE, "%s: load + init first", fn);
+    if (which != FMS_USERS && which != FMS_ITEMS) return fail(ctx, FMS_ERR_INVALID_ARG, "%s: which = %d", fn, which);
+    if (n_chunks < 1 || chunk < 0 || chunk >= n_chunks) return fail(ctx, FMS_ERR_INVALID_ARG, "%s: chunk %d of %d", fn, chunk, n_chunks);
     const int64_t n = which == FMS_USERS ? A.n_users : A.n_items;
-    const int64_t rb = std::min<int64_t>(n, A.shard_rows[which] * A.shard_index);
-    const int64_t re = std::min<int64_t>(n, rb + A.shard_rows[which]);
-    FMS_CUDA(ctx, cudaMemsetAsync(A.info.p, 0, sizeof(int), ctx->stream));
+    const int64_t S = A.shard_rows[which];
+    const int64_t c = (S + n_chunks - 1) / n_chunks;                       // rows per chunk, the same on every rank
+    const int64_t sb = S * A.shard_index;
+    const int64_t rb = std::min<int64_t>(n, sb + std::min<int64_t>(S, c * chunk));
+    const int64_t re = std::min<int64_t>(n, sb + std::min<int64_t>(S, c * (chunk + 1)));
+    if (chunk == 0) FMS_CUDA(ctx, cudaMemsetAsync(A.info.p, 0, sizeof(int), ctx->stream));
     bool tc = false;
     if (A.kernel != FMS_ALS_KERNEL_GENERIC) tc = als_tc_supported(ctx, A.rank) != 0;
     if (A.kernel == FMS_ALS_KERNEL_TC && !tc) return fail(ctx, FMS_ERR_UNSUPPORTED, "tensor-core ALS kernel does not cover rank %d", A.rank);
@@ -149,6 +154,16 @@ FMS_API int fms_als_half_step(fms_ctx *ctx, int which, double lambda) {
     else FMS_TRY(als_launch_half_step_generic(ctx, which, (float)lambda, rb, re));
     A.last_bad = -1;
     return FMS_OK;
+}
+
+FMS_API int fms_als_half_step(fms_ctx *ctx, int which, double lambda) {
+    CHECK_CTX(ctx);
+    return als_half_step_rows(ctx, which, lambda, 0, 1, "fms_als_half_step");
+}
+
+FMS_API int fms_als_half_step_chunk(fms_ctx *ctx, int which, double lambda, int chunk, int n_chunks) {
+    CHECK_CTX(ctx);
+    return als_half_step_rows(ctx, which, lambda, chunk, n_chunks, "fms_als_half_step_chunk");
 }
 
 FMS_API int fms_als_last_info(fms_ctx *ctx, int64_t *bad_rows) {
@@ -191,6 +206,26 @@ FMS_API int fms_als_planes_device(fms_ctx *ctx, int which, void **hi, void **lo,
     if (which != 0 && which != 1) return fail(ctx, FMS_ERR_INVALID_ARG, "which = %d", which);
     if (!als_tc_supported(ctx, A.rank)) return fail(ctx, FMS_ERR_UNSUPPORTED, "no gather planes at rank %d", A.rank);
     return als_tc_planes(ctx, which, hi, lo, rows_padded);
+}
+
+FMS_API int fms_als_planes_ipc_handle(fms_ctx *ctx, int which, void *handle64) {
+    CHECK_CTX(ctx);
+    AlsState &A = ctx->als;
+    if (!A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_planes_ipc_handle: init first");
+    if ((which != FMS_USERS && which != FMS_ITEMS) || !handle64) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_planes_ipc_handle: bad arguments");
+    if (!als_tc_supported(ctx, A.rank)) return fail(ctx, FMS_ERR_UNSUPPORTED, "no gather planes at rank %d", A.rank);
+    return als_tc_ipc_handle(ctx, which, handle64);
+}
+
+FMS_API int fms_als_planes_open_peers(fms_ctx *ctx, int which, const void *handles, int n) {
+    CHECK_CTX(ctx);
+    AlsState &A = ctx->als;
+    if (!A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_planes_open_peers: init first");
+    if (which != FMS_USERS && which != FMS_ITEMS) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_planes_open_peers: which = %d", which);
+    if (!als_tc_supported(ctx, A.rank)) return fail(ctx, FMS_ERR_UNSUPPORTED, "no gather planes at rank %d", A.rank);
+    if (n == 0) { als_tc_close_peers(ctx, which); return FMS_OK; }
+    if (!handles) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_planes_open_peers: handles is null");
+    return als_tc_open_peers(ctx, which, handles, n);
 }
 
 FMS_API int fms_als_planes_updated(fms_ctx *ctx, int which) {

@@ -68,6 +68,11 @@ struct AlsState {
     DevBuf<uint16_t> plane[2];
     bool plane_valid[2] = {false, false};
     int64_t plane_rows[2] = {0, 0};
+    // peer-to-peer exchange: device table of every rank's plane base for a side (own pointer at own index), filled from
+    // CUDA IPC handles; the solver warps then store each new plane row into all replicas over NVLink
+    DevBuf<unsigned long long> peer_tab[2];
+    void *peer_open[2][64] = {};
+    int peer_n[2] = {0, 0};
     // tensor-core path: ratings re-laid in 16-rating stages per row (padded), see als_tc.cu
     DevBuf<int32_t> stage_ptr[2];            // per row: first stage (exclusive scan of ceil(n_row / 16)), N + 1 entries
     DevBuf<int32_t> colp[2];                 // 16 * total_stages partner indices (padding -> zero row of the planes)
@@ -219,6 +224,9 @@ int als_launch_half_step_tc(fms_ctx *ctx, int which, float lambda, int64_t row_b
 int als_tc_refresh_planes(fms_ctx *ctx, int which);
 int als_tc_dump(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t re, float *d_dump);
 int als_tc_planes(fms_ctx *ctx, int s, void **hi, void **lo, int64_t *rows_padded);
+int als_tc_ipc_handle(fms_ctx *ctx, int s, void *handle64);
+int als_tc_open_peers(fms_ctx *ctx, int s, const void *handles, int n);
+void als_tc_close_peers(fms_ctx *ctx, int s);
 int als_predict_device(fms_ctx *ctx, const int64_t *d_u, const int64_t *d_i, int64_t n, double *d_out, uint8_t *d_found);
 int als_ensure_fac64(fms_ctx *ctx);
 int svm_launch_sweep(fms_ctx *ctx, int64_t local_iterations);

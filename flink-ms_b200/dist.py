@@ -3,7 +3,10 @@
 ALS: every rank holds the full CSR pair and full factor replicas, solves the row shard
 [g*S, (g+1)*S) of the side being updated, then the shards are ALL-GATHERED into every replica -- the exchange
 Flink does with a join + coGroup network shuffle between half-steps (Appendix A.1 `updateFactors` message
-build).  Per-row arithmetic is identical to the 1-GPU run, so results are bitwise equal.
+build).  Per-row arithmetic is identical to the 1-GPU run, so results are bitwise equal.  On GPUs the shard is
+solved in up to `max_chunks` chunks and chunk k's all-gather runs on a second stream under the solve of chunk k+1;
+or -- `ContextALSBackend.enable_p2p` -- the kernel itself stores each solved row into every rank's replica over NVLink
+(CUDA IPC mappings), and only a barrier follows the half-step.
 
 SVM: rank g sweeps the CoCoA blocks k with k % G == g; the per-rank sum of block deltas (dim floats) is
 ALL-REDUCED and every rank applies w += (stepsize / blocks) * delta -- FlinkML's broadcast of w and
@@ -44,9 +47,13 @@ class ContextALSBackend:
         self.ctx = ctx
         self.device = device
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+        self.p2p = False
 
     def half_step(self, which, lam):
         self.ctx.als_half_step(which, lam)
+
+    def half_step_chunk(self, which, lam, chunk, n_chunks):
+        self.ctx.als_half_step_chunk(which, lam, chunk, n_chunks)
 
     def factor_tensor(self, which, rank):
         ptr, rows_padded, b, e = self.ctx.als_factors_device(which)
@@ -54,6 +61,34 @@ class ContextALSBackend:
 
     def updated(self, which):
         self.ctx.als_factors_updated(which)
+
+    def enable_p2p(self, group=None):
+        """Map every rank's gather planes into this process (CUDA IPC) so that the half-step kernel writes its plane rows
+        into all replicas itself.  Returns False when the tensor-core path (and so the planes) is not in use."""
+        world = dist.get_world_size(group)
+        try:
+            for which in (0, 1):
+                mine = self.ctx.als_planes_ipc_handle(which)
+                handles = [None] * world
+                dist.all_gather_object(handles, mine, group=group)
+                self.ctx.als_planes_open_peers(which, b"".join(handles), world)
+        except Exception:  # noqa: BLE001  (FMS_ERR_UNSUPPORTED: generic kernel in use; IPC not available)
+            for which in (0, 1):
+                try:
+                    self.ctx.als_planes_open_peers(which, b"", 0)
+                except Exception:  # noqa: BLE001
+                    pass
+            self.p2p = False
+            ok = torch.zeros(1, device=self.device)
+        else:
+            self.p2p = True
+            ok = torch.ones(1, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)           # all ranks or none
+        if ok.item() == 0 and self.p2p:
+            for which in (0, 1):
+                self.ctx.als_planes_open_peers(which, b"", 0)
+            self.p2p = False
+        return self.p2p
 
     def plane_tensors(self, which, rank):
         """fp16 views of the gather planes as a tuple of tensors to all-gather, or None when the tensor-core path does
@@ -71,12 +106,17 @@ class ContextALSBackend:
 class DistributedALS:
     """iterate(T){ users = f(items); items = f(users) }; users = f(items), sharded by rows."""
 
-    def __init__(self, backend, rank_dim: int, group=None):
+    def __init__(self, backend, rank_dim: int, group=None, max_chunks: int = 4, min_chunk_rows: int = 1024):
         self.b = backend
         self.rank_dim = rank_dim
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._stale = set()
+        self.max_chunks = max_chunks
+        self.min_chunk_rows = min_chunk_rows
+        self._comm = None
+        self._scratch = None
+        self._tok = None
 
     def _gather(self, full):
         s = full.shape[0] // self.world
@@ -110,9 +150,59 @@ class DistributedALS:
             self._gather(self.b.factor_tensor(which, self.rank_dim))
         self._stale.clear()
 
+    def _token(self):
+        if self._tok is None:
+            self._tok = torch.zeros(1, device=self.b.device)
+        return self._tok
+
+    def _overlap_plan(self, which):
+        """(planes, K) when the half-step can be pipelined: K equal chunks of the shard, chunk k's all-gather running on
+        a second stream while chunk k+1 is being solved."""
+        if self.world == 1 or self.max_chunks < 2 or not hasattr(self.b, "half_step_chunk") or getattr(self.b, "stream", None) is None:
+            return None, 1
+        planes = self.b.plane_tensors(which, self.rank_dim) if hasattr(self.b, "plane_tensors") else None
+        if planes is None:
+            return None, 1
+        s = planes[0].shape[0] // self.world
+        k = next((k for k in range(self.max_chunks, 1, -1) if s % k == 0 and s // k >= self.min_chunk_rows), 1)
+        return planes, k
+
     def half_step(self, which, lam):
-        self.b.half_step(which, lam)
-        self.exchange(which)
+        if self.world > 1 and getattr(self.b, "p2p", False):
+            # the kernel stored every solved plane row into all replicas over NVLink: only a barrier is left
+            self.b.half_step(which, lam)
+            with torch.cuda.stream(self.b.stream):
+                dist.all_reduce(self._token(), group=self.group)
+            self.b.planes_updated(which)
+            self._stale.add(which)
+            return
+        planes, K = self._overlap_plan(which)
+        if K == 1:
+            self.b.half_step(which, lam)
+            self.exchange(which)
+            return
+        full = planes[0]                                                 # [world * S, 2 * rank] fp16
+        S = full.shape[0] // self.world
+        c = S // K
+        me = dist.get_rank(self.group)
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=full.device)
+        if self._scratch is None or self._scratch.shape != (self.world * c, full.shape[1]):
+            self._scratch = torch.empty((self.world * c, full.shape[1]), dtype=full.dtype, device=full.device)
+        grid = full.view(self.world, S, full.shape[1])
+        for k in range(K):
+            self.b.half_step_chunk(which, lam, k, K)                     # solver kernel on the library's stream
+            ev = torch.cuda.Event()
+            ev.record(self.b.stream)
+            with torch.cuda.stream(self._comm):
+                self._comm.wait_event(ev)
+                dist.all_gather_into_tensor(self._scratch, full[me * S + k * c: me * S + (k + 1) * c], group=self.group)
+                grid[:, k * c:(k + 1) * c].copy_(self._scratch.view(self.world, c, full.shape[1]))
+        done = torch.cuda.Event()
+        done.record(self._comm)
+        self.b.stream.wait_event(done)                                   # the next half-step reads the gathered planes
+        self.b.planes_updated(which)
+        self._stale.add(which)
 
     def iteration(self, lam):
         self.half_step(0, lam)

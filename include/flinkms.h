@@ -104,6 +104,10 @@ FMS_API int fms_als_load(fms_ctx *ctx, const int64_t *user, const int64_t *item,
 FMS_API int fms_als_init(fms_ctx *ctx, int rank, int64_t seed);
 /* One updateFactors pass over this rank's shard: which = FMS_USERS solves users from items. */
 FMS_API int fms_als_half_step(fms_ctx *ctx, int which, double lambda);
+/* The same update restricted to chunk `chunk` of `n_chunks` equal row ranges of this rank's shard (c = ceil(S /
+ * n_chunks) rows each, identical on every rank), so a sharded host can all-gather chunk k on a second stream while
+ * chunk k+1 is being solved.  All chunks 0 .. n_chunks-1 together equal one fms_als_half_step. */
+FMS_API int fms_als_half_step_chunk(fms_ctx *ctx, int which, double lambda, int chunk, int n_chunks);
 /* Device view of a factor matrix for collectives: fp32 row-major, rows_padded = S * shard_count rows of
  * `rank` floats; shard rows are [shard_begin, shard_end). */
 FMS_API int fms_als_factors_device(fms_ctx *ctx, int which, void **dev_ptr, int64_t *rows_padded,
@@ -118,6 +122,14 @@ FMS_API int fms_als_factors_updated(fms_ctx *ctx, int which);
  * half-steps instead of the fp32 matrix (same bytes, no re-split afterwards) and call fms_als_planes_updated; it
  * must then all-gather the fp32 matrix once before reading factors out. */
 FMS_API int fms_als_planes_device(fms_ctx *ctx, int which, void **hi, void **lo, int64_t *rows_padded);
+/* Peer-to-peer exchange instead of a collective (one process per GPU on one NVLink node): every rank exports the CUDA
+ * IPC handle (64 bytes) of its plane buffer for a side, the host gathers the handles in rank order and hands the table
+ * to every rank.  From then on the half-step kernel stores each solved row's plane row into EVERY replica (posted
+ * NVLink writes from the solver warps), so no all-gather follows the half-step: the host only needs a barrier across
+ * ranks (and fms_als_planes_updated) before the next half-step.  n = 0 unmaps the peers again.  Mappings die with
+ * the buffers: re-exchange handles after fms_als_load / fms_als_init with a different geometry. */
+FMS_API int fms_als_planes_ipc_handle(fms_ctx *ctx, int which, void *handle64);
+FMS_API int fms_als_planes_open_peers(fms_ctx *ctx, int which, const void *handles, int n);
 FMS_API int fms_als_planes_updated(fms_ctx *ctx, int which);
 /* number of rows whose Cholesky hit a non-positive pivot in the last half-step (dposv info != 0; FlinkML
  * ignores it, so do we -- exposed for tests). */

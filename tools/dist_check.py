@@ -19,18 +19,25 @@ torch.cuda.set_device(lr)
 dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)
 ok = True
-for d in (64, 16):                                   # tensor-core path (plane exchange) and generic path (fp32 exchange)
-    u, i, r = synth.als_ratings(3001, 403, 90_000, seed=5)
+# tensor-core path with plain and with chunked / overlapped plane exchange, generic path (fp32 exchange)
+for d, chunks in ((64, 1), (64, 4), (64, 0), (16, 1)):          # chunks 0: peer-to-peer plane stores from the kernel
+    u, i, r = synth.als_ratings(3001 if chunks == 1 else 4096, 403 if chunks == 1 else 512, 90_000, seed=5)
     ctx = fms.Context(lr)
     ctx.als_load(u, i, r, rank, world)
     ctx.als_init(d, 42)
-    D.DistributedALS(D.ContextALSBackend(ctx, dev), d).fit(3, 0.9)
+    be = D.ContextALSBackend(ctx, dev)
+    if chunks == 0:
+        assert be.enable_p2p(), "peer mapping failed"
+    dals = D.DistributedALS(be, d, max_chunks=max(chunks, 1), min_chunk_rows=8)
+    dals.fit(3, 0.9)
+    if chunks > 1:
+        assert dals._overlap_plan(0)[1] > 1, "chunked exchange was not exercised"
     Xs, Ys = ctx.als_get_factors(0)[1], ctx.als_get_factors(1)[1]
     ref = fms.Context(lr)
     ref.als_fit(u, i, r, d, 3, 0.9, 42)
     X1, Y1 = ref.als_get_factors(0)[1], ref.als_get_factors(1)[1]
     same = np.array_equal(Xs, X1) and np.array_equal(Ys, Y1)
-    print(f"[rank {rank}] ALS rank {d}: sharded == single: {same}  max diff {np.abs(Xs - X1).max():.3e}", flush=True)
+    print(f"[rank {rank}] ALS rank {d} chunks {chunks}: sharded == single: {same}  max diff {np.abs(Xs - X1).max():.3e}", flush=True)
     ok &= same
     ctx.close(); ref.close()
 n, dim, K = 20000, 256, 24
