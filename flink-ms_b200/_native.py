@@ -38,6 +38,7 @@ SIGNATURES = {
     "fms_launch_count": (C.c_int64, [_vp]),
     "fms_als_fit": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int64, _i64p, _i64p]),
     "fms_als_get_factors": (C.c_int, [_vp, C.c_int, _i64p, _f64p]),
+    "fms_als_get_factor_rows": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, _i64p, _f64p]),
     "fms_als_set_model": (C.c_int, [_vp, _i64p, _f64p, C.c_int64, _i64p, _f64p, C.c_int64, C.c_int]),
     "fms_als_predict": (C.c_int, [_vp, _i64p, _i64p, C.c_int64, _f64p, _u8p]),
     "fms_als_mse": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64, _f64p, _i64p]),
@@ -171,6 +172,25 @@ class Context:
                                            shard_count, C.byref(nu), C.byref(ni)))
         self._als_shape = (nu.value, ni.value, 0)
         return nu.value, ni.value
+
+    def als_load_device(self, user_ptr, item_ptr, rating_ptr, nnz, shard_index=0, shard_count=1):
+        """fms_als_load with DEVICE pointers (int64, int64, float64 arrays of nnz elements already in HBM)."""
+        nu, ni = C.c_int64(), C.c_int64()
+        self._check(self._lib.fms_als_load(self._h, C.cast(C.c_void_p(user_ptr), _i64p), C.cast(C.c_void_p(item_ptr), _i64p),
+                                           C.cast(C.c_void_p(rating_ptr), _f64p), nnz, shard_index, shard_count, C.byref(nu), C.byref(ni)))
+        self._als_shape = (nu.value, ni.value, 0)
+        return nu.value, ni.value
+
+    def als_get_factor_rows(self, which, row_begin, row_end, ids_out=None, factors_out=None):
+        """Rows [row_begin, row_end) of a side (a rank's own shard): ids and float64 factors, optionally into caller buffers."""
+        rank = self._als_shape[2]
+        m = row_end - row_begin
+        ids = np.empty(m, np.int64) if ids_out is None else ids_out
+        fac = np.empty((m, rank), np.float64) if factors_out is None else factors_out
+        if ids.dtype != np.int64 or fac.dtype != np.float64 or ids.size < m or fac.size < m * rank or not fac.flags.c_contiguous:
+            raise ValueError("als_get_factor_rows: output buffers have the wrong dtype / size")
+        self._check(self._lib.fms_als_get_factor_rows(self._h, which, row_begin, row_end, _p(ids, _i64p), _p(fac, _f64p)))
+        return ids[:m], fac.reshape(-1, rank)[:m] if fac.ndim == 1 else fac[:m]
 
     def als_init(self, rank, seed):
         self._check(self._lib.fms_als_init(self._h, rank, seed))

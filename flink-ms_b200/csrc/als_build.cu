@@ -116,6 +116,7 @@ static int build_side(fms_ctx *ctx, int side, const int32_t *d_row, const int32_
     return FMS_OK;
 }
 
+// h_user / h_item / h_rating: host OR device pointers (unified addressing decides the copy direction)
 int als_build_csr(fms_ctx *ctx, const int64_t *h_user, const int64_t *h_item, const double *h_rating, int64_t nnz) {
     AlsState &A = ctx->als;
     cudaStream_t st = ctx->stream;
@@ -130,9 +131,9 @@ int als_build_csr(fms_ctx *ctx, const int64_t *h_user, const int64_t *h_item, co
     FMS_CUDA(ctx, d_item.alloc((size_t)nnz));
     FMS_CUDA(ctx, d_r64.alloc((size_t)nnz));
     FMS_CUDA(ctx, d_r32.alloc((size_t)nnz));
-    FMS_CUDA(ctx, cudaMemcpyAsync(d_user.p, h_user, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
-    FMS_CUDA(ctx, cudaMemcpyAsync(d_item.p, h_item, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
-    FMS_CUDA(ctx, cudaMemcpyAsync(d_r64.p, h_rating, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+    FMS_CUDA(ctx, cudaMemcpyAsync(d_user.p, h_user, (size_t)nnz * 8, cudaMemcpyDefault, st));
+    FMS_CUDA(ctx, cudaMemcpyAsync(d_item.p, h_item, (size_t)nnz * 8, cudaMemcpyDefault, st));
+    FMS_CUDA(ctx, cudaMemcpyAsync(d_r64.p, h_rating, (size_t)nnz * 8, cudaMemcpyDefault, st));
     if (nnz > 0) {
         k_f64_to_f32<<<grid_for(nnz, T), T, 0, st>>>(d_r64.p, nnz, d_r32.p);
         FMS_LAUNCH_CHECK(ctx);

@@ -266,6 +266,23 @@ FMS_API int fms_als_get_factors(fms_ctx *ctx, int which, int64_t *ids, double *f
     return FMS_OK;
 }
 
+FMS_API int fms_als_get_factor_rows(fms_ctx *ctx, int which, int64_t row_begin, int64_t row_end, int64_t *ids, double *factors) {
+    CHECK_CTX(ctx);
+    AlsState &A = ctx->als;
+    if (!A.inited && !A.model_external) return fail(ctx, FMS_ERR_STATE, "The ALS model has not been fitted.");
+    if (which != 0 && which != 1) return fail(ctx, FMS_ERR_INVALID_ARG, "which = %d", which);
+    const int64_t n = which == 0 ? A.n_users : A.n_items;
+    if (row_begin < 0 || row_end < row_begin || row_end > n) return fail(ctx, FMS_ERR_INVALID_ARG, "rows [%lld, %lld) of %lld", (long long)row_begin, (long long)row_end, (long long)n);
+    const int64_t m = row_end - row_begin;
+    if (ids && m) FMS_CUDA(ctx, cudaMemcpyAsync(ids, A.ids[which].p + row_begin, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (factors && m) {
+        FMS_TRY(als_ensure_fac64(ctx));
+        FMS_CUDA(ctx, cudaMemcpyAsync(factors, A.fac64[which].p + row_begin * A.rank, (size_t)m * A.rank * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
 FMS_API int fms_als_set_model(fms_ctx *ctx, const int64_t *user_ids, const double *user_factors, int64_t n_users,
                               const int64_t *item_ids, const double *item_factors, int64_t n_items, int rank) {
     CHECK_CTX(ctx);

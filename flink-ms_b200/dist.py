@@ -40,6 +40,23 @@ def shard_range(n: int, world: int, rank: int):
     return b, min(n, b + s), s
 
 
+def sharded_upload(host_arrays, device, group=None):
+    """Each rank copies 1/G of every host array (pinned torch tensors of equal length) to its GPU and the slices are
+    all-gathered over NVLink: every rank ends up with the full arrays in HBM having pulled only 1/G over PCIe."""
+    world, me = dist.get_world_size(group), dist.get_rank(group)
+    out = []
+    for h in host_arrays:
+        n = h.numel()
+        s = (n + world - 1) // world
+        full = torch.empty(s * world, dtype=h.dtype, device=device)
+        b, e = min(n, s * me), min(n, s * (me + 1))
+        mine = full[s * me: s * (me + 1)]
+        mine[: e - b].copy_(h[b:e], non_blocking=True)
+        dist.all_gather_into_tensor(full, mine, group=group)
+        out.append(full[:n])
+    return out
+
+
 class ContextALSBackend:
     """Adapts a `_native.Context` (ratings already loaded with this rank's shard) to DistributedALS."""
 
@@ -208,11 +225,14 @@ class DistributedALS:
         self.half_step(0, lam)
         self.half_step(1, lam)
 
-    def fit(self, iterations, lam):
+    def fit(self, iterations, lam, finalize=True):
+        """finalize=False leaves the fp32 matrices sharded (every rank's own shard is current): enough when each rank
+        emits its own rows, like the parallel sinks of the reference job."""
         for _ in range(iterations):
             self.iteration(lam)
         self.half_step(0, lam)
-        self.finalize()
+        if finalize:
+            self.finalize()
 
 
 class ContextSVMBackend:

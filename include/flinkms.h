@@ -83,6 +83,10 @@ FMS_API int fms_als_fit(fms_ctx *ctx, const int64_t *user, const int64_t *item, 
                         /*out*/ int64_t *n_users, int64_t *n_items);
 /* (ids ascending, row-major N x rank doubles).  Either out pointer may be NULL. */
 FMS_API int fms_als_get_factors(fms_ctx *ctx, int which, int64_t *ids, double *factors);
+/* The same for the rows [row_begin, row_end) of a side (dense row index = position of the id in ascending order):
+ * what one rank of a sharded run emits for its own shard [S * g, S * (g + 1)) -- those rows are current on that
+ * rank without the final all-gather of the fp32 matrices. */
+FMS_API int fms_als_get_factor_rows(fms_ctx *ctx, int which, int64_t row_begin, int64_t row_end, int64_t *ids, double *factors);
 /* Install an externally trained model (e.g. parsed `id,U|I,f1;f2;...` rows, ALSImpl.scala:84) for predict. */
 FMS_API int fms_als_set_model(fms_ctx *ctx, const int64_t *user_ids, const double *user_factors, int64_t n_users,
                               const int64_t *item_ids, const double *item_factors, int64_t n_items, int rank);
@@ -98,7 +102,8 @@ FMS_API int fms_als_mse(fms_ctx *ctx, const int64_t *u, const int64_t *i, const 
 /* --- step-level ALS API: data resident in HBM, used by bench.py (`value`) and by the one-process-per-GPU
  *     sharded driver (flink-ms_b200/dist.py), which all-gathers the factor shards between half-steps. --- */
 /* Upload + index the ratings.  Every rank holds the full CSR pair and full factor replicas and SOLVES only
- * rows [shard_index*S, (shard_index+1)*S) with S = ceil(N / shard_count). */
+ * rows [shard_index*S, (shard_index+1)*S) with S = ceil(N / shard_count).  user / item / rating may be host OR
+ * device pointers (a sharded host uploads 1/G of the triples per rank and all-gathers them over NVLink first). */
 FMS_API int fms_als_load(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t nnz,
                          int shard_index, int shard_count, /*out*/ int64_t *n_users, int64_t *n_items);
 FMS_API int fms_als_init(fms_ctx *ctx, int rank, int64_t seed);

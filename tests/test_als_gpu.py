@@ -270,3 +270,52 @@ def test_tensor_core_and_generic_kernels_agree_over_iterations(fms, ctx):
         out[name] = (ctx.als_get_factors(0)[1], ctx.als_get_factors(1)[1])
     ctx.als_set_kernel(fms._native.ALS_KERNEL_AUTO)
     assert rel_err(out["tc"][0], out["generic"][0]) <= 5e-5 and rel_err(out["tc"][1], out["generic"][1]) <= 5e-5
+
+
+@pytest.mark.parametrize("rank", [8, 64])
+def test_chunked_half_step_equals_full(fms, ctx, rank):
+    """fms_als_half_step_chunk over all chunks == one fms_als_half_step (the pipelined exchange of dist.py relies on it)."""
+    u, i, r = _case(fms, 1000, 150, 20000, seed=21)
+    ctx.als_load(u, i, r)
+    ctx.als_init(rank, 42)
+    ctx.als_half_step(0, 0.9)
+    ctx.als_half_step(1, 0.9)
+    _, Xref = ctx.als_get_factors(0)
+    _, Yref = ctx.als_get_factors(1)
+    c2 = fms.Context(0)
+    c2.als_load(u, i, r)
+    c2.als_init(rank, 42)
+    for which in (0, 1):
+        for k in range(3):
+            c2.als_half_step_chunk(which, 0.9, k, 3)
+    _, X = c2.als_get_factors(0)
+    _, Y = c2.als_get_factors(1)
+    assert np.array_equal(X, Xref) and np.array_equal(Y, Yref)
+    with pytest.raises(fms.FlinkMSError):
+        c2.als_half_step_chunk(0, 0.9, 3, 3)
+    c2.close()
+
+
+def test_factor_rows_and_device_pointer_load(fms, ctx):
+    """fms_als_get_factor_rows returns slices of fms_als_get_factors; fms_als_load accepts device pointers."""
+    import torch
+    u, i, r = _case(fms, 500, 120, 9000, seed=22)
+    ctx.als_fit(u, i, r, 16, 2, 0.9, 42)
+    ids, X = ctx.als_get_factors(0)
+    for b, e in ((0, len(ids)), (17, 203), (5, 5)):
+        ids_s, Xs = ctx.als_get_factor_rows(0, b, e)
+        assert np.array_equal(ids_s, ids[b:e]) and np.array_equal(Xs, X[b:e])
+    with pytest.raises(fms.FlinkMSError):
+        ctx.als_get_factor_rows(0, 0, len(ids) + 1)
+    du, di, dr = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (u.astype(np.int64), i.astype(np.int64), r.astype(np.float64)))
+    torch.cuda.synchronize()
+    c2 = fms.Context(0)
+    assert c2.als_load_device(du.data_ptr(), di.data_ptr(), dr.data_ptr(), len(u)) == (len(ids), len(np.unique(i)))
+    c2.als_init(16, 42)
+    for _ in range(2):
+        c2.als_half_step(0, 0.9)
+        c2.als_half_step(1, 0.9)
+    c2.als_half_step(0, 0.9)
+    ids2, X2 = c2.als_get_factors(0)
+    assert np.array_equal(ids2, ids) and np.array_equal(X2, X)
+    c2.close()
