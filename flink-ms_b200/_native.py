@@ -39,6 +39,7 @@ SIGNATURES = {
     "fms_als_fit": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int64, _i64p, _i64p]),
     "fms_als_get_factors": (C.c_int, [_vp, C.c_int, _i64p, _f64p]),
     "fms_als_get_factor_rows": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, _i64p, _f64p]),
+    "fms_als_sgd_step": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64, C.c_double, C.c_double, C.c_double, _f64p, _f64p, C.c_int, _f64p, _f64p]),
     "fms_als_set_model": (C.c_int, [_vp, _i64p, _f64p, C.c_int64, _i64p, _f64p, C.c_int64, C.c_int]),
     "fms_als_predict": (C.c_int, [_vp, _i64p, _i64p, C.c_int64, _f64p, _u8p]),
     "fms_als_mse": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64, _f64p, _i64p]),
@@ -253,6 +254,23 @@ class Context:
         self._check(self._lib.fms_als_set_model(self._h, _p(ui, _i64p), _p(uf, _f64p), len(ui), _p(ii, _i64p),
                                                 _p(itf, _f64p), len(ii), rank))
         self._als_shape = (len(ui), len(ii), rank)
+
+    def als_sgd_step(self, user, item, rating, learning_rate=0.1, user_reg=0.0, item_reg=0.0, user_mean=None, item_mean=None, apply=False):
+        """One micro-batch of the als-ms online SGD (SGD.java:160-217): returns (updated_user_rows, updated_item_rows)."""
+        u, i, r = _i64(user), _i64(item), _f64(rating)
+        if not (len(u) == len(i) == len(r)):
+            raise ValueError("user/item/rating lengths differ")
+        rank = self._als_shape[2]
+        um = None if user_mean is None else _f64(user_mean)
+        im = None if item_mean is None else _f64(item_mean)
+        if (um is not None and len(um) != rank) or (im is not None and len(im) != rank):
+            raise ValueError("mean vectors must have `rank` entries")
+        ou = np.empty((len(u), rank), np.float64)
+        oi = np.empty((len(u), rank), np.float64)
+        self._check(self._lib.fms_als_sgd_step(self._h, _p(u, _i64p), _p(i, _i64p), _p(r, _f64p), len(u), learning_rate, user_reg, item_reg,
+                                               None if um is None else _p(um, _f64p), None if im is None else _p(im, _f64p),
+                                               1 if apply else 0, _p(ou, _f64p), _p(oi, _f64p)))
+        return ou, oi
 
     def als_predict(self, u, i, out=None, found=None):
         """Batched lookup-and-dot.  `out` (float64) / `found` (uint8) may be caller-owned buffers, e.g. pinned host memory

@@ -238,4 +238,102 @@ int als_predict_device(fms_ctx *ctx, const int64_t *d_u, const int64_t *d_i, int
     return FMS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ N2 online SGD step
+// als-ms SGD.java:160-217.  One warp per rating; every record reads the model as it was before the batch.  All
+// arithmetic is fp64 with the reference's operation order and NO fused multiply-add (Java rounds every operation), so the
+// emitted rows are bit-identical to the Java code's for the same fp64 model.
+__device__ __forceinline__ int64_t find_id(const int64_t *__restrict__ ids, int64_t n, int64_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (ids[mid] < key) lo = mid + 1; else hi = mid; }
+    return (lo < n && ids[lo] == key) ? lo : -1;
+}
+
+__global__ void k_als_sgd(const int64_t *__restrict__ qu, const int64_t *__restrict__ qi, const double *__restrict__ qr, int64_t n,
+                          const int64_t *__restrict__ uids, int64_t nu, const int64_t *__restrict__ iids, int64_t ni,
+                          const double *__restrict__ U, const double *__restrict__ I, const double *__restrict__ umean,
+                          const double *__restrict__ imean, int d, double lr, double ureg, double ireg, double *__restrict__ out_u,
+                          double *__restrict__ out_i, int64_t *__restrict__ row_u, int64_t *__restrict__ row_i,
+                          int *__restrict__ win_u, int *__restrict__ win_i) {
+    const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (k >= n) return;
+    int64_t a = -1, b = -1;
+    if (lane == 0) { a = find_id(uids, nu, qu[k]); b = find_id(iids, ni, qi[k]); }
+    a = __shfl_sync(0xffffffffu, a, 0);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    const double *x = a >= 0 ? U + a * d : umean, *y = b >= 0 ? I + b * d : imean;   // cold start: the MEAN rows (SGD.java:171-172)
+    double xs[4], ys[4];                                               // rank <= 128: four components per lane
+    double pred = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int j = lane + 32 * t;
+        xs[t] = j < d ? x[j] : 0.0;
+        ys[t] = j < d ? y[j] : 0.0;
+    }
+    for (int j = 0; j < d; ++j) {                                      // prediction += u[j] * v[j], in index order
+        const double p = __dmul_rn(xs[j >> 5], ys[j >> 5]);
+        pred = __dadd_rn(pred, __shfl_sync(0xffffffffu, p, j & 31));
+    }
+    const double err = __dsub_rn(qr[k], pred);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int j = lane + 32 * t;
+        if (j < d) {
+            out_u[k * d + j] = __dadd_rn(xs[t], __dmul_rn(lr, __dsub_rn(__dmul_rn(err, ys[t]), __dmul_rn(ureg, xs[t]))));
+            out_i[k * d + j] = __dadd_rn(ys[t], __dmul_rn(lr, __dsub_rn(__dmul_rn(err, xs[t]), __dmul_rn(ireg, ys[t]))));
+        }
+    }
+    if (lane == 0) {
+        row_u[k] = a; row_i[k] = b;
+        if (win_u && a >= 0) atomicMax(win_u + a, (int)k);            // the last record of an id wins, as in the Kafka consumer
+        if (win_i && b >= 0) atomicMax(win_i + b, (int)k);
+    }
+}
+
+__global__ void k_als_sgd_apply(int64_t n, int d, const double *__restrict__ out, const int64_t *__restrict__ row, const int *__restrict__ win,
+                                double *__restrict__ F64, float *__restrict__ F32) {
+    const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (k >= n) return;
+    const int64_t r = row[k];
+    if (r < 0 || win[r] != (int)k) return;
+    for (int j = lane; j < d; j += 32) {
+        const double v = out[k * d + j];
+        F64[r * d + j] = v;
+        if (F32) F32[r * d + j] = (float)v;
+    }
+}
+
+int als_sgd_step_device(fms_ctx *ctx, const int64_t *d_u, const int64_t *d_i, const double *d_r, int64_t n, double lr, double ureg,
+                        double ireg, const double *d_umean, const double *d_imean, int apply, double *d_out_u, double *d_out_i) {
+    AlsState &A = ctx->als;
+    if (n <= 0) return FMS_OK;
+    if (n >= ((int64_t)1 << 31)) return fail(ctx, FMS_ERR_UNSUPPORTED, "sgd batch too large");
+    DevBuf<int64_t> row_u, row_i;
+    DevBuf<int> win_u, win_i;
+    FMS_CUDA(ctx, row_u.alloc((size_t)n));
+    FMS_CUDA(ctx, row_i.alloc((size_t)n));
+    if (apply) {
+        FMS_CUDA(ctx, win_u.alloc((size_t)A.n_users + 1));
+        FMS_CUDA(ctx, win_i.alloc((size_t)A.n_items + 1));
+        FMS_CUDA(ctx, cudaMemsetAsync(win_u.p, 0xff, win_u.bytes(), ctx->stream));
+        FMS_CUDA(ctx, cudaMemsetAsync(win_i.p, 0xff, win_i.bytes(), ctx->stream));
+    }
+    const unsigned grid = (unsigned)((n * 32 + 255) / 256);
+    k_als_sgd<<<grid, 256, 0, ctx->stream>>>(d_u, d_i, d_r, n, A.ids[0].p, A.n_users, A.ids[1].p, A.n_items, A.fac64[0].p, A.fac64[1].p,
+                                             d_umean, d_imean, A.rank, lr, ureg, ireg, d_out_u, d_out_i, row_u.p, row_i.p,
+                                             apply ? win_u.p : nullptr, apply ? win_i.p : nullptr);
+    FMS_LAUNCH_CHECK(ctx);
+    if (apply) {
+        const bool f32 = A.inited;                                     // a fitted (fp32) model is kept in step with its fp64 copy
+        k_als_sgd_apply<<<grid, 256, 0, ctx->stream>>>(n, A.rank, d_out_u, row_u.p, win_u.p, A.fac64[0].p, f32 ? A.fac[0].p : nullptr);
+        FMS_LAUNCH_CHECK(ctx);
+        k_als_sgd_apply<<<grid, 256, 0, ctx->stream>>>(n, A.rank, d_out_i, row_i.p, win_i.p, A.fac64[1].p, f32 ? A.fac[1].p : nullptr);
+        FMS_LAUNCH_CHECK(ctx);
+        A.plane_valid[0] = A.plane_valid[1] = false;
+    }
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
 }  // namespace fms

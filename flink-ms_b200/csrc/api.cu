@@ -380,6 +380,37 @@ FMS_API int fms_als_mse(fms_ctx *ctx, const int64_t *u, const int64_t *i, const 
     return FMS_OK;
 }
 
+FMS_API int fms_als_sgd_step(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t n, double learning_rate,
+                             double user_reg, double item_reg, const double *user_mean, const double *item_mean, int apply,
+                             double *out_user, double *out_item) {
+    CHECK_CTX(ctx);
+    AlsState &A = ctx->als;
+    if (!A.inited && !A.model_external) return fail(ctx, FMS_ERR_STATE, "The ALS model has not been fitted.");
+    if (n < 0 || (n && (!user || !item || !rating || !out_user || !out_item))) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_sgd_step: null argument or n < 0");
+    if (!user_mean || !item_mean) return fail(ctx, FMS_ERR_INVALID_ARG, "Unable to load User mean or item mean factors.");   // SGD.java:150-152
+    if (n == 0) return FMS_OK;
+    FMS_TRY(als_ensure_fac64(ctx));
+    const int d = A.rank;
+    DevBuf<int64_t> du, di;
+    DevBuf<double> dr, dmean, dou, doi;
+    FMS_CUDA(ctx, du.alloc((size_t)n));
+    FMS_CUDA(ctx, di.alloc((size_t)n));
+    FMS_CUDA(ctx, dr.alloc((size_t)n));
+    FMS_CUDA(ctx, dmean.alloc((size_t)2 * d));
+    FMS_CUDA(ctx, dou.alloc((size_t)n * d));
+    FMS_CUDA(ctx, doi.alloc((size_t)n * d));
+    FMS_CUDA(ctx, cudaMemcpyAsync(du.p, user, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMS_CUDA(ctx, cudaMemcpyAsync(di.p, item, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMS_CUDA(ctx, cudaMemcpyAsync(dr.p, rating, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMS_CUDA(ctx, cudaMemcpyAsync(dmean.p, user_mean, (size_t)d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMS_CUDA(ctx, cudaMemcpyAsync(dmean.p + d, item_mean, (size_t)d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FMS_TRY(als_sgd_step_device(ctx, du.p, di.p, dr.p, n, learning_rate, user_reg, item_reg, dmean.p, dmean.p + d, apply, dou.p, doi.p));
+    FMS_CUDA(ctx, cudaMemcpyAsync(out_user, dou.p, (size_t)n * d * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMS_CUDA(ctx, cudaMemcpyAsync(out_item, doi.p, (size_t)n * d * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
 // ====================================================================================================== SVM
 __global__ void k_f64_to_f32_chunk(const double *__restrict__ in, int64_t n, float *__restrict__ out) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

@@ -221,6 +221,8 @@ int als_launch_init(fms_ctx *ctx, int64_t seed);
 int als_launch_half_step_generic(fms_ctx *ctx, int which, float lambda, int64_t row_begin, int64_t row_end);
 int als_tc_supported(const fms_ctx *ctx, int rank);
 int als_launch_half_step_tc(fms_ctx *ctx, int which, float lambda, int64_t row_begin, int64_t row_end);
+int als_sgd_step_device(fms_ctx *ctx, const int64_t *d_u, const int64_t *d_i, const double *d_r, int64_t n, double lr, double ureg,
+                        double ireg, const double *d_umean, const double *d_imean, int apply, double *d_out_u, double *d_out_i);
 int als_tc_refresh_planes(fms_ctx *ctx, int which);
 int als_tc_dump(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t re, float *d_dump);
 int als_tc_planes(fms_ctx *ctx, int s, void **hi, void **lo, int64_t *rows_padded);

@@ -151,6 +151,48 @@ class ALS:
         raise NotImplementedError("ALS.empiricalRisk is never called by the reference (SURVEY.md Appendix A.1)")
 
 
+class OnlineSGD:
+    """The per-rating update of the als-ms `SGD` job (als-ms/.../qs/SGD.java:160-217) as a micro-batch operator over a
+    GPU-resident model.  Parameter names are the job's CLI flags (`learningRate`, `userRegularization`,
+    `itemRegularization`, `userMean`, `itemMean` as "f1;f2;..." strings, SGD.java:143-147, :160-166).  `step` returns the
+    records the reference would send to Kafka: "id,U,f1;f2;..." then "id,I,f1;f2;..." per rating (SGD.java:209-216)."""
+
+    def __init__(self, ctx: N.Context, params: dict | None = None):
+        self._ctx = ctx
+        p = dict(params or {})
+        self.learningRate = float(p.get("learningRate", 0.1))
+        self.userRegularization = float(p.get("userRegularization", 0.0))
+        self.itemRegularization = float(p.get("itemRegularization", 0.0))
+        self.userMean = self._vec(p.get("userMean"))
+        self.itemMean = self._vec(p.get("itemMean"))
+
+    @staticmethod
+    def _vec(v):
+        if v is None:
+            return None
+        if isinstance(v, str):
+            return np.array([float(t) for t in v.split(";")], np.float64)
+        return np.asarray(v, np.float64)
+
+    def step(self, ratings, apply: bool = True):
+        """ratings: (user[], item[], rating[]) arrays or an iterable of (user, item, rating) triples."""
+        from .formats import als_factor_row
+        if isinstance(ratings, tuple) and len(ratings) == 3 and not np.isscalar(ratings[0]):
+            user, item, rating = ratings
+        else:
+            arr = list(ratings)
+            user = [t[0] for t in arr]; item = [t[1] for t in arr]; rating = [t[2] for t in arr]
+        if self.userMean is None or self.itemMean is None:
+            raise RuntimeError("Unable to load User mean or item mean factors.")   # IllegalStateException, SGD.java:150-152
+        ou, oi = self._ctx.als_sgd_step(user, item, rating, self.learningRate, self.userRegularization, self.itemRegularization,
+                                        self.userMean, self.itemMean, apply)
+        out = []
+        for k in range(len(ou)):
+            out.append(als_factor_row(user[k], "U", ou[k]))
+            out.append(als_factor_row(item[k], "I", oi[k]))
+        return out
+
+
 class DenseVector:
     """org.apache.flink.ml.math.DenseVector: `.data` is the Array[Double] (SVMImpl.scala:34; SGDV0.java:258)."""
 

@@ -99,6 +99,20 @@ FMS_API int fms_als_predict(fms_ctx *ctx, const int64_t *u, const int64_t *i, in
 FMS_API int fms_als_mse(fms_ctx *ctx, const int64_t *u, const int64_t *i, const double *rating, int64_t n,
                         double *mse, int64_t *n_used);
 
+/* Online SGD step of the als-ms job (als-ms/.../qs/SGD.java:160-217) for a micro-batch of n ratings against the
+ * model resident in the ctx (fitted, or installed with fms_als_set_model).  For rating k: u = U[user_k] (user_mean
+ * when the id is not in the model, SGD.java:171), v = I[item_k] (item_mean); e = r - u.v; u' = u + lr (e v - reg_u u);
+ * v' = v + lr (e u - reg_i v) -- both from the ORIGINAL u, v (SGD.java:199-207; SGDV0 differs).  out_user / out_item
+ * (n x rank doubles) receive the two records the reference emits per rating.  Every record reads the model as it was
+ * before the batch (what the reference sees while a batch's updates are still travelling through Kafka); with
+ * apply != 0 the rows of known ids are then overwritten, the LAST record of an id winning as in the Kafka consumer
+ * (ALSKafkaConsumer.java:78-92); records of unknown ids are returned but not inserted.  fp64, Java operation order,
+ * no fused multiply-add: rows are bit-identical to the Java arithmetic on the same fp64 model.  Missing mean vectors
+ * are an error like the reference's IllegalStateException. */
+FMS_API int fms_als_sgd_step(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t n,
+                             double learning_rate, double user_reg, double item_reg, const double *user_mean,
+                             const double *item_mean, int apply, double *out_user, double *out_item);
+
 /* --- step-level ALS API: data resident in HBM, used by bench.py (`value`) and by the one-process-per-GPU
  *     sharded driver (flink-ms_b200/dist.py), which all-gathers the factor shards between half-steps. --- */
 /* Upload + index the ratings.  Every rank holds the full CSR pair and full factor replicas and SOLVES only

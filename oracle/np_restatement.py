@@ -123,3 +123,38 @@ def svm_fit(X, y, block_id, blocks, iterations, local_iterations, lam=1.0, steps
     for k in range(blocks):
         alpha[members[k]] = alphas[k]
     return w, alpha
+
+
+def sgd_step(user_ids, U, item_ids, I, users, items, ratings, learning_rate=0.1, user_reg=0.0, item_reg=0.0,
+             user_mean=None, item_mean=None, apply=False):
+    """als-ms online SGD for a micro-batch (als-ms/src/main/java/de/tub/it4bi/modelserving/qs/SGD.java:160-217), fp64,
+    Java operation order (every operation rounded, no fused multiply-add: plain Python floats do exactly that).
+    Snapshot semantics: every record reads the model as it was before the batch.  Returns (out_user, out_item, U', I');
+    with apply the last record of a known id overwrites its row (ALSKafkaConsumer.java:78-92), unknown ids are not
+    inserted.  PARITY UNPINNED like the rest of oracle/ (the reference has no tests for this path)."""
+    user_ids = np.asarray(user_ids, np.int64); item_ids = np.asarray(item_ids, np.int64)
+    U = np.asarray(U, np.float64); I = np.asarray(I, np.float64)
+    if user_mean is None or item_mean is None:
+        raise ValueError("Unable to load User mean or item mean factors.")       # SGD.java:150-152
+    d = U.shape[1] if U.size else I.shape[1]
+    n = len(users)
+    ou = np.empty((n, d)); oi = np.empty((n, d))
+    U2, I2 = U.copy(), I.copy()
+    for k in range(n):
+        a = int(np.searchsorted(user_ids, users[k])); a = a if a < len(user_ids) and user_ids[a] == users[k] else -1
+        b = int(np.searchsorted(item_ids, items[k])); b = b if b < len(item_ids) and item_ids[b] == items[k] else -1
+        x = [float(v) for v in (U[a] if a >= 0 else user_mean)]
+        y = [float(v) for v in (I[b] if b >= 0 else item_mean)]
+        pred = 0.0
+        for j in range(d):
+            pred += x[j] * y[j]
+        err = float(ratings[k]) - pred
+        for j in range(d):
+            ou[k, j] = x[j] + learning_rate * (err * y[j] - user_reg * x[j])
+            oi[k, j] = y[j] + learning_rate * (err * x[j] - item_reg * y[j])
+        if apply:
+            if a >= 0:
+                U2[a] = ou[k]
+            if b >= 0:
+                I2[b] = oi[k]
+    return ou, oi, U2, I2

@@ -319,3 +319,50 @@ def test_factor_rows_and_device_pointer_load(fms, ctx):
     ids2, X2 = c2.als_get_factors(0)
     assert np.array_equal(ids2, ids) and np.array_equal(X2, X)
     c2.close()
+
+
+def test_online_sgd_step_bit_exact_against_restatement(fms, ctx):
+    """N2: fms_als_sgd_step == the Java arithmetic of SGD.java:160-217 (restated in oracle/np_restatement.sgd_step), bit for
+    bit: snapshot reads, mean-vector cold start, last record wins on apply, unknown ids returned but not inserted."""
+    from oracle import np_restatement as npr
+    rng = np.random.default_rng(5)
+    for rank in (5, 64, 100):
+        uid = np.array([3, 7, 8, 20, 21, 1000], np.int64)
+        iid = np.array([-4, 0, 5, 9], np.int64)
+        U = rng.standard_normal((len(uid), rank))
+        I = rng.standard_normal((len(iid), rank))
+        um, im = U.mean(0), I.mean(0)
+        ctx.als_set_model(uid, U, iid, I)
+        users = np.array([7, 7, 3, 999, 20, 7, 1000, 8], np.int64)            # 999: unknown user; 7 three times
+        items = np.array([0, 5, 5, 9, 123, 0, -4, 9], np.int64)               # 123: unknown item
+        ratings = rng.uniform(1, 5, len(users))
+        ou, oi = ctx.als_sgd_step(users, items, ratings, 0.05, 0.01, 0.02, um, im, apply=False)
+        ru, ri, _, _ = npr.sgd_step(uid, U, iid, I, users, items, ratings, 0.05, 0.01, 0.02, um, im, apply=False)
+        assert np.array_equal(ou, ru) and np.array_equal(oi, ri)
+        _, U0 = ctx.als_get_factors(0)
+        assert np.array_equal(U0, U)                                            # apply=False leaves the model alone
+        ou, oi = ctx.als_sgd_step(users, items, ratings, 0.05, 0.01, 0.02, um, im, apply=True)
+        ru, ri, U2, I2 = npr.sgd_step(uid, U, iid, I, users, items, ratings, 0.05, 0.01, 0.02, um, im, apply=True)
+        assert np.array_equal(ou, ru) and np.array_equal(oi, ri)
+        ids_u, Ug = ctx.als_get_factors(0)
+        ids_i, Ig = ctx.als_get_factors(1)
+        assert np.array_equal(ids_u, uid) and np.array_equal(ids_i, iid)        # nothing inserted
+        assert np.array_equal(Ug, U2) and np.array_equal(Ig, I2)
+    with pytest.raises(fms.FlinkMSError):
+        ctx.als_sgd_step(users, items, ratings, 0.05, 0.0, 0.0, None, im)
+
+
+def test_online_sgd_operator_emits_reference_records(fms, ctx):
+    from oracle import np_restatement as npr
+    formats = __import__("importlib").import_module("flink-ms_b200.formats")
+    uid = np.array([1, 2], np.int64); iid = np.array([10, 11], np.int64)
+    U = np.array([[0.5, -1.25], [2.0, 0.125]]); I = np.array([[1.0, 3.0], [-0.75, 0.2]])
+    ctx.als_set_model(uid, U, iid, I)
+    sgd = fms.OnlineSGD(ctx, {"learningRate": "0.1", "userMean": "0.1;0.2", "itemMean": "0.3;0.4"})
+    recs = sgd.step([(1, 11, 4.0), (5, 10, 2.5)], apply=False)
+    ru, ri, _, _ = npr.sgd_step(uid, U, iid, I, [1, 5], [11, 10], [4.0, 2.5], 0.1, 0.0, 0.0, [0.1, 0.2], [0.3, 0.4])
+    assert recs == [formats.als_factor_row(1, "U", ru[0]), formats.als_factor_row(11, "I", ri[0]),
+                    formats.als_factor_row(5, "U", ru[1]), formats.als_factor_row(10, "I", ri[1])]
+    assert recs[0].startswith("1,U,") and recs[1].startswith("11,I,")
+    with pytest.raises(RuntimeError):
+        fms.OnlineSGD(ctx, {}).step([(1, 11, 4.0)])

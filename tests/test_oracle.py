@@ -192,3 +192,24 @@ def test_svm_predict_strict_threshold():
     w = np.array([2.0, 5.0])
     assert oracle.svm_predict(X, w, 0.0, False).tolist() == [1.0, -1.0, -1.0]      # raw == threshold -> -1
     assert oracle.svm_predict(X, w, 0.0, True).tolist() == [2.0, 0.0, -2.0]
+
+
+def test_sgd_restatement_properties():
+    """oracle/np_restatement.sgd_step: zero learning rate is the identity, zero regularisation moves u along v, the last
+    record of an id wins on apply, unknown ids use the mean rows and are not inserted."""
+    from oracle import np_restatement as npr
+    uid = np.array([1, 4], np.int64); iid = np.array([2], np.int64)
+    U = np.array([[1.0, 2.0], [0.5, -1.0]]); I = np.array([[3.0, -1.0]])
+    um, im = np.array([0.1, 0.1]), np.array([0.2, 0.2])
+    ou, oi, U2, I2 = npr.sgd_step(uid, U, iid, I, [1], [2], [5.0], 0.0, 0.3, 0.3, um, im, apply=True)
+    assert np.array_equal(ou[0], U[0]) and np.array_equal(oi[0], I[0]) and np.array_equal(U2, U)
+    ou, oi, _, _ = npr.sgd_step(uid, U, iid, I, [1], [2], [5.0], 0.1, 0.0, 0.0, um, im)
+    err = 5.0 - (1.0 * 3.0 + 2.0 * -1.0)
+    assert np.allclose(ou[0], U[0] + 0.1 * err * I[0]) and np.allclose(oi[0], I[0] + 0.1 * err * U[0])
+    ou, oi, U2, I2 = npr.sgd_step(uid, U, iid, I, [1, 9, 1], [2, 2, 7], [5.0, 1.0, 2.0], 0.1, 0.0, 0.0, um, im, apply=True)
+    assert np.array_equal(U2[0], ou[2]) and np.array_equal(I2[0], oi[1])          # last record of user 1 / item 2 wins
+    assert np.array_equal(U2[1], U[1]) and U2.shape == U.shape                    # user 9 not inserted
+    e9 = 1.0 - float(um @ I[0])
+    assert np.allclose(ou[1], um + 0.1 * e9 * I[0])                               # cold start from the mean row
+    with pytest.raises(ValueError):
+        npr.sgd_step(uid, U, iid, I, [1], [2], [5.0], 0.1, 0.0, 0.0, None, im)
