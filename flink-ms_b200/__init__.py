@@ -5,6 +5,6 @@ name), so import it as `import flinkms_b200` (shim at the repo root) or
 """
 from . import _native
 from ._native import Context, FlinkMSError
-from .operators import ALS, SVM, DenseVector, Factors, OnlineSGD, ParameterMap
+from .operators import ALS, SVM, DenseVector, Factors, OnlineSGD, ParameterMap, readCsvFile, readLibSVM
 
-__all__ = ["ALS", "SVM", "DenseVector", "Factors", "OnlineSGD", "ParameterMap", "Context", "FlinkMSError", "_native"]
+__all__ = ["ALS", "SVM", "DenseVector", "Factors", "OnlineSGD", "ParameterMap", "readCsvFile", "readLibSVM", "Context", "FlinkMSError", "_native"]

@@ -40,6 +40,8 @@ SIGNATURES = {
     "fms_als_get_factors": (C.c_int, [_vp, C.c_int, _i64p, _f64p]),
     "fms_als_get_factor_rows": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, _i64p, _f64p]),
     "fms_als_sgd_step": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64, C.c_double, C.c_double, C.c_double, _f64p, _f64p, C.c_int, _f64p, _f64p]),
+    "fms_parse_ratings_csv": (C.c_int, [_vp, C.c_char_p, C.c_int64, C.c_char, C.c_int, _i64p, _i64p, _f64p, C.c_int64, _i64p]),
+    "fms_parse_libsvm": (C.c_int, [_vp, C.c_char_p, C.c_int64, _f64p, C.c_int64, _i64p, _i32p, _f64p, C.c_int64, _i64p, _i64p, _i32p]),
     "fms_als_set_model": (C.c_int, [_vp, _i64p, _f64p, C.c_int64, _i64p, _f64p, C.c_int64, C.c_int]),
     "fms_als_predict": (C.c_int, [_vp, _i64p, _i64p, C.c_int64, _f64p, _u8p]),
     "fms_als_mse": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64, _f64p, _i64p]),
@@ -254,6 +256,29 @@ class Context:
         self._check(self._lib.fms_als_set_model(self._h, _p(ui, _i64p), _p(uf, _f64p), len(ui), _p(ii, _i64p),
                                                 _p(itf, _f64p), len(ii), rank))
         self._als_shape = (len(ui), len(ii), rank)
+
+    # ---- N4 ingest
+    def parse_ratings_csv(self, text: bytes, delimiter: str = ",", ignore_first_line: bool = False):
+        """env.readCsvFile[(Int, Int, Double)] on the device: bytes -> (user int64[], item int64[], rating float64[])."""
+        n = C.c_int64()
+        d = delimiter.encode()
+        if len(d) != 1:
+            raise ValueError("single-byte field delimiter expected")
+        self._check(self._lib.fms_parse_ratings_csv(self._h, text, len(text), d, int(ignore_first_line), None, None, None, 0, C.byref(n)))
+        u = np.empty(n.value, np.int64); i = np.empty(n.value, np.int64); r = np.empty(n.value, np.float64)
+        self._check(self._lib.fms_parse_ratings_csv(self._h, text, len(text), d, int(ignore_first_line), _p(u, _i64p), _p(i, _i64p),
+                                                    _p(r, _f64p), n.value, C.byref(n)))
+        return u, i, r
+
+    def parse_libsvm(self, text: bytes):
+        """env.readLibSVM on the device: bytes -> (label float64[], (ptr int64[], idx int32[], val float64[]), dim)."""
+        n, nnz, dim = C.c_int64(), C.c_int64(), C.c_int32()
+        self._check(self._lib.fms_parse_libsvm(self._h, text, len(text), None, 0, None, None, None, 0, C.byref(n), C.byref(nnz), C.byref(dim)))
+        y = np.empty(n.value, np.float64); ptr = np.empty(n.value + 1, np.int64)
+        idx = np.empty(nnz.value, np.int32); val = np.empty(nnz.value, np.float64)
+        self._check(self._lib.fms_parse_libsvm(self._h, text, len(text), _p(y, _f64p), n.value, _p(ptr, _i64p), _p(idx, _i32p), _p(val, _f64p),
+                                               nnz.value, C.byref(n), C.byref(nnz), C.byref(dim)))
+        return y, (ptr, idx, val), dim.value
 
     def als_sgd_step(self, user, item, rating, learning_rate=0.1, user_reg=0.0, item_reg=0.0, user_mean=None, item_mean=None, apply=False):
         """One micro-batch of the als-ms online SGD (SGD.java:160-217): returns (updated_user_rows, updated_item_rows)."""

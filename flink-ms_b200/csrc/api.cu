@@ -411,6 +411,22 @@ FMS_API int fms_als_sgd_step(fms_ctx *ctx, const int64_t *user, const int64_t *i
     return FMS_OK;
 }
 
+// ====================================================================================================== N4 ingest
+FMS_API int fms_parse_ratings_csv(fms_ctx *ctx, const char *text, int64_t nbytes, char delimiter, int ignore_first_line, int64_t *user,
+                                  int64_t *item, double *rating, int64_t capacity, int64_t *n_rows) {
+    CHECK_CTX(ctx);
+    if (nbytes < 0 || (nbytes && !text) || capacity < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_parse_ratings_csv: bad arguments");
+    if (delimiter == '\n' || delimiter == '\r') return fail(ctx, FMS_ERR_INVALID_ARG, "fms_parse_ratings_csv: the field delimiter cannot be a line break");
+    return ingest_ratings_csv(ctx, text, nbytes, delimiter, ignore_first_line, user, item, rating, capacity, n_rows);
+}
+
+FMS_API int fms_parse_libsvm(fms_ctx *ctx, const char *text, int64_t nbytes, double *label, int64_t row_capacity, int64_t *csr_ptr,
+                             int32_t *csr_idx, double *csr_val, int64_t nnz_capacity, int64_t *n_rows, int64_t *nnz, int32_t *dim) {
+    CHECK_CTX(ctx);
+    if (nbytes < 0 || (nbytes && !text) || row_capacity < 0 || nnz_capacity < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_parse_libsvm: bad arguments");
+    return ingest_libsvm(ctx, text, nbytes, label, row_capacity, csr_ptr, csr_idx, csr_val, nnz_capacity, n_rows, nnz, dim);
+}
+
 // ====================================================================================================== SVM
 __global__ void k_f64_to_f32_chunk(const double *__restrict__ in, int64_t n, float *__restrict__ out) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

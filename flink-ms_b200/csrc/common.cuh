@@ -223,6 +223,10 @@ int als_tc_supported(const fms_ctx *ctx, int rank);
 int als_launch_half_step_tc(fms_ctx *ctx, int which, float lambda, int64_t row_begin, int64_t row_end);
 int als_sgd_step_device(fms_ctx *ctx, const int64_t *d_u, const int64_t *d_i, const double *d_r, int64_t n, double lr, double ureg,
                         double ireg, const double *d_umean, const double *d_imean, int apply, double *d_out_u, double *d_out_i);
+int ingest_ratings_csv(fms_ctx *ctx, const char *text, int64_t nbytes, char delimiter, int ignore_first_line, int64_t *user, int64_t *item,
+                       double *rating, int64_t capacity, int64_t *n_rows);
+int ingest_libsvm(fms_ctx *ctx, const char *text, int64_t nbytes, double *label, int64_t row_capacity, int64_t *csr_ptr, int32_t *csr_idx,
+                  double *csr_val, int64_t nnz_capacity, int64_t *n_rows, int64_t *nnz, int32_t *dim);
 int als_tc_refresh_planes(fms_ctx *ctx, int which);
 int als_tc_dump(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t re, float *d_dump);
 int als_tc_planes(fms_ctx *ctx, int s, void **hi, void **lo, int64_t *rows_padded);

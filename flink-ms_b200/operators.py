@@ -151,6 +151,20 @@ class ALS:
         raise NotImplementedError("ALS.empiricalRisk is never called by the reference (SURVEY.md Appendix A.1)")
 
 
+def readCsvFile(ctx: N.Context, filePath: str, fieldDelimiter: str = ",", ignoreFirstLine: bool = False):
+    """env.readCsvFile[(Int, Int, Double)](filePath, fieldDelimiter = ..., ignoreFirstLine = ...) of ALSImpl.scala:29-32,
+    parsed on the GPU (row N4): returns the (user[], item[], rating[]) arrays ALS.fit takes."""
+    with open(filePath, "rb") as f:
+        return ctx.parse_ratings_csv(f.read(), fieldDelimiter, ignoreFirstLine)
+
+
+def readLibSVM(ctx: N.Context, filePath: str):
+    """env.readLibSVM(filePath) of SVMImpl.scala:21 (FlinkML MLUtils.readLibSVM), parsed on the GPU (row N4): returns
+    (labels, (csr_ptr, csr_idx, csr_val), dimension) -- the sparse LabeledVector data set as CSR."""
+    with open(filePath, "rb") as f:
+        return ctx.parse_libsvm(f.read())
+
+
 class OnlineSGD:
     """The per-rating update of the als-ms `SGD` job (als-ms/.../qs/SGD.java:160-217) as a micro-batch operator over a
     GPU-resident model.  Parameter names are the job's CLI flags (`learningRate`, `userRegularization`,

@@ -113,6 +113,22 @@ FMS_API int fms_als_sgd_step(fms_ctx *ctx, const int64_t *user, const int64_t *i
                              double learning_rate, double user_reg, double item_reg, const double *user_mean,
                              const double *item_mean, int apply, double *out_user, double *out_item);
 
+/* --- N4: GPU-side ingest of the text the reference jobs read before training.  `text` may be a host or a device
+ *     pointer; outputs likewise.  Call once with all output pointers NULL to size the buffers (*n_rows, *nnz). --- */
+/* env.readCsvFile[(Int, Int, Double)](input, fieldDelimiter, ignoreFirstLine) (ALSImpl.scala:22-32): one
+ * `user<delim>item<delim>rating` record per line (\n or \r\n), empty lines skipped, further columns ignored.
+ * Integers as Integer.parseInt, doubles as Double.parseDouble for decimal literals (correctly rounded: Clinger fast
+ * path + Eisel-Lemire).  A malformed line -> FMS_ERR_INVALID_ARG, a literal the parser cannot round exactly (exact
+ * half-way cases, subnormals, hex floats) -> FMS_ERR_UNSUPPORTED, both naming the line; no CPU fallback. */
+FMS_API int fms_parse_ratings_csv(fms_ctx *ctx, const char *text, int64_t nbytes, char delimiter, int ignore_first_line,
+                                  int64_t *user, int64_t *item, double *rating, int64_t capacity, int64_t *n_rows);
+/* env.readLibSVM(training) (SVMImpl.scala:21; FlinkML MLUtils.readLibSVM): `label idx:val idx:val ...`, '#' starts
+ * a comment, blank lines skipped, indices 1-based in the file and 0-based in csr_idx, *dim = largest index seen.
+ * Output is the CSR triple fms_svm_fit / fms_svm_load take (FMS_X_CSR_F64) plus the labels. */
+FMS_API int fms_parse_libsvm(fms_ctx *ctx, const char *text, int64_t nbytes, double *label, int64_t row_capacity,
+                             int64_t *csr_ptr, int32_t *csr_idx, double *csr_val, int64_t nnz_capacity, int64_t *n_rows,
+                             int64_t *nnz, int32_t *dim);
+
 /* --- step-level ALS API: data resident in HBM, used by bench.py (`value`) and by the one-process-per-GPU
  *     sharded driver (flink-ms_b200/dist.py), which all-gathers the factor shards between half-steps. --- */
 /* Upload + index the ratings.  Every rank holds the full CSR pair and full factor replicas and SOLVES only
