@@ -1,6 +1,6 @@
 """Summarise an `ncu --set full` report (run here, where ncu can read .ncu-rep files) into the small JSON files kept
 under profiles/: per-kernel duration, DRAM bytes, pipe utilisation, issue activity, L2 hit rate.
-usage: python tools/ncu_extract.py gpurun_out/final.ncu-rep profiles/r01_ncu_final_kernels.json [profiles/r01_traffic.json]"""
+usage: python tools/ncu_extract.py profiles/r01_ncu_final_kernels.json profiles/r01_traffic.json gpurun_out/final.ncu-rep [more.ncu-rep ...]"""
 import csv
 import io
 import json
@@ -29,26 +29,27 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us":
 
 
 def main():
-    rep, out = sys.argv[1], sys.argv[2]
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(txt)))
-    hdr, units = rows[0], rows[1]
+    out, traffic_out, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
     res = []
-    for r in rows[2:]:
-        d = {"kernel": r[hdr.index("Kernel Name")], "id": r[hdr.index("ID")]}
-        for m, k in WANT.items():
-            if m in hdr:
-                i = hdr.index(m)
-                try:
-                    v = float(r[i].replace(",", ""))
-                except ValueError:
-                    continue
-                d[k] = v * UNIT.get(units[i], 1.0) if k in ("duration", "dram_read", "dram_write") else v
-        res.append(d)
+    for rep in reps:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(txt)))
+        hdr, units = rows[0], rows[1]
+        for r in rows[2:]:
+            d = {"kernel": r[hdr.index("Kernel Name")], "id": r[hdr.index("ID")], "report": rep}
+            for m, k in WANT.items():
+                if m in hdr:
+                    i = hdr.index(m)
+                    try:
+                        v = float(r[i].replace(",", ""))
+                    except ValueError:
+                        continue
+                    d[k] = v * UNIT.get(units[i], 1.0) if k in ("duration", "dram_read", "dram_write") else v
+            res.append(d)
     json.dump(res, open(out, "w"), indent=1)
     for d in res:
         print(d["kernel"][:60], {k: (round(v, 4) if isinstance(v, float) else v) for k, v in d.items() if k not in ("kernel",)})
-    if len(sys.argv) > 3:
+    if traffic_out:
         tr = {"source": "ncu --set full --clock-control none, python bench.py --steps 1 (" + out + ")"}
         tc = [d for d in res if "k_als_rows_tc64" in d["kernel"]]
         sv = [d for d in res if "k_svm_sweep_warp" in d["kernel"]]
@@ -57,7 +58,7 @@ def main():
             tr["als_half_step_items"] = tc[1]["dram_read"] + tc[1]["dram_write"]
         if sv:
             tr["svm_block_sweep"] = sv[0]["dram_read"] + sv[0]["dram_write"]
-        json.dump(tr, open(sys.argv[3], "w"), indent=1)
+        json.dump(tr, open(traffic_out, "w"), indent=1)
         print(tr)
 
 
