@@ -1,24 +1,29 @@
 // als_tc.cu -- K1 on the 5th-generation tensor cores (rank 64): warp-specialised persistent kernel, one CTA per SM.
 //
-// Data layout in HBM: besides the fp32 factor matrix every side keeps two fp16 "gather planes" hi = f16(x) and
-// lo = f16((x - hi) * 2^11) (64 halves = 128 B per row each).  hi + lo * 2^-11 carries ~22 mantissa bits, so
-// the Gramian  hi hi^T + 2^-11 (hi lo^T + lo hi^T)  is fp32-grade (plain fp16 / tf32 would be 2^-11: not enough
-// for the 1e-4 parity target) while every product is exact in the fp32 accumulator.
+// Data layout in HBM: besides the fp32 factor matrix every side keeps its fp16 "gather planes" hi = f16(x) and
+// lo = f16((x - hi) * 2^11), interleaved as one 256-byte row per factor row (64 hi halves, then 64 lo halves).
+// hi + lo * 2^-11 carries ~22 mantissa bits, so the Gramian  hi hi^T + 2^-11 (hi lo^T + lo hi^T)  is fp32-grade
+// (plain fp16 / tf32 would be 2^-11: not enough for the 1e-4 parity target) while every product is exact in the fp32
+// accumulator.  The ratings are pre-laid as 16-entry stages (rows padded with a zero plane row).
 //
-//   producer warp  : reads the CSR slice of 16 ratings (coalesced), issues TMA gather4 loads of the 16 partner
-//                    rows of both planes straight into the UMMA MN-major / 128-byte-swizzle stage (no registers, no
-//                    per-rating SM instructions), and writes the ratings as two extra 64-wide operand chunks
+// 28 warps, register budgets set per role with setmaxnreg:
+//   producers (6-7): stream the stage layout, issue TMA gather4 loads of the 16 partner rows (hi half and lo half of
+//                    the plane row) straight into the UMMA MN-major / 128-byte-swizzle stage -- no registers, no
+//                    per-rating SM instructions -- and write the ratings as two 16-byte column groups R, R' of a
+//                    third operand chunk.  Stage = 6 KB, ring of 13, mbarrier full / empty.
 //   MMA warp       : per stage two tcgen05.mma (kind::f16, M=64, K=16):
-//                        D[:,   0:192] (+)= hi [hi | lo | R ]^T        (N = 192)
-//                        D[:, 64:192]   += lo [hi |      R']^T        (N = 128, leading-dim offset skips `lo`)
+//                        D[:,   0:136] (+)= hi [hi | lo | R ]^T        (N = 136)
+//                        D[:, 64:136]   += lo [hi |      R']^T        (N = 72, leading-dim offset skips `lo`)
 //                    => cols 0-63 hi hi^T, 64-127 hi lo^T + lo hi^T, col 128 sum r_hi*hi, col 129 the 2^-11 terms of
 //                    b = Y^T r.  Accumulators live in TMEM (2 slots x 256 columns).
-//   epilogue warps : tcgen05.ld one TMEM lane quadrant each, G = D1 + 2^-11 D2 (+ lambda n on the diagonal), b, and
-//                    hand the system to a solver warp through shared memory
-//   solver warps   : 8 warps, one system each: two matrix rows per lane in registers, right-looking Cholesky in 16
-//                    rank-4 panel steps (two loops, packed FFMA2, register window rotated inside the last update of
-//                    a panel), L columns kept in the hand-off buffer, fused forward substitution, column-sweep back
-//                    substitution; writes x_u (fp32) and its two gather planes.
+//   epilogue (4)   : tcgen05.ld one TMEM lane quadrant each, G = D1 + 2^-11 D2 (+ lambda n on the diagonal) as a packed
+//                    lower triangle, b, handed to a solver warp through one of 16 shared-memory buffers
+//   solvers (16)   : one system per warp, ONE matrix row per lane at a time (32 data registers): 32x32 Cholesky of
+//                    A11 in 8 rank-4 panels (pivot block by shuffle, factored redundantly per lane, packed FFMA2
+//                    trailing updates against broadcast LDS.128, register window rotated inside the last update
+//                    of a panel), private triangular solve per row for L21, syrk on the A22 row, the same 32x32
+//                    loop for A22, fused forward substitution, two-half blocked back substitution; writes x (fp32)
+//                    and its plane row -- into every rank's replica when peers are mapped (NVLink stores).
 //
 // Takes over the FlinkML `updateFactors` coGroup body (entered from
 // flink-als/src/main/scala/de/tub/it4bi/ALSImpl.scala:52), same math as k_als_rows_generic (als_kernels.cu).
