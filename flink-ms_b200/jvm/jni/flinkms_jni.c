@@ -69,6 +69,54 @@ JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_alsPredict(JNIEnv *env, jcla
     check(env, ctx, fms_als_predict(ctx, buf(env, u), buf(env, i), n, buf(env, out), buf(env, found)));
 }
 
+JNIEXPORT jdoubleArray JNICALL Java_de_tub_it4bi_gpu_Native_alsMse(JNIEnv *env, jclass cls, jlong c, jobject u, jobject i, jobject rating,
+                                                                 jlong n) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    double mse = 0.0;
+    int64_t used = 0;
+    if (check(env, ctx, fms_als_mse(ctx, buf(env, u), buf(env, i), buf(env, rating), n, &mse, &used))) return NULL;
+    jdouble r[2] = {mse, (jdouble)used};
+    jdoubleArray out = (*env)->NewDoubleArray(env, 2);
+    if (out) (*env)->SetDoubleArrayRegion(env, out, 0, 2, r);
+    return out;
+}
+
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_alsSgdStep(JNIEnv *env, jclass cls, jlong c, jobject user, jobject item, jobject rating,
+                                                               jlong n, jdouble lr, jdouble ureg, jdouble ireg, jobject umean, jobject imean,
+                                                               jboolean apply, jobject outUser, jobject outItem) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    check(env, ctx, fms_als_sgd_step(ctx, buf(env, user), buf(env, item), buf(env, rating), n, lr, ureg, ireg, buf(env, umean),
+                                     buf(env, imean), apply ? 1 : 0, buf(env, outUser), buf(env, outItem)));
+}
+
+JNIEXPORT jlong JNICALL Java_de_tub_it4bi_gpu_Native_parseRatingsCsv(JNIEnv *env, jclass cls, jlong c, jobject text, jlong nbytes,
+                                                                     jbyte delimiter, jboolean ignoreFirst, jobject user, jobject item,
+                                                                     jobject rating, jlong capacity) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    int64_t rows = 0;
+    if (check(env, ctx, fms_parse_ratings_csv(ctx, buf(env, text), nbytes, (char)delimiter, ignoreFirst ? 1 : 0, buf(env, user),
+                                              buf(env, item), buf(env, rating), capacity, &rows))) return -1;
+    return rows;
+}
+
+JNIEXPORT jlongArray JNICALL Java_de_tub_it4bi_gpu_Native_parseLibSvm(JNIEnv *env, jclass cls, jlong c, jobject text, jlong nbytes,
+                                                                      jobject label, jlong rowCapacity, jobject csrPtr, jobject csrIdx,
+                                                                      jobject csrVal, jlong nnzCapacity) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    int64_t rows = 0, nnz = 0;
+    int32_t dim = 0;
+    if (check(env, ctx, fms_parse_libsvm(ctx, buf(env, text), nbytes, buf(env, label), rowCapacity, buf(env, csrPtr), buf(env, csrIdx),
+                                         buf(env, csrVal), nnzCapacity, &rows, &nnz, &dim))) return NULL;
+    jlong r[3] = {rows, nnz, dim};
+    jlongArray out = (*env)->NewLongArray(env, 3);
+    if (out) (*env)->SetLongArrayRegion(env, out, 0, 3, r);
+    return out;
+}
+
 JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_svmFit(JNIEnv *env, jclass cls, jlong c, jobject x, jint xDtype, jobject csrPtr,
                                                            jobject csrIdx, jobject y, jlong n, jint dim, jobject blockId, jint blocks,
                                                            jint iterations, jlong localIterations, jdouble regularization,

@@ -43,6 +43,27 @@ public final class Native implements AutoCloseable {
         svmPredict(ctx, x, xDtype, csrPtr, csrIdx, n, dim, w, threshold, outputDecisionFunction, out);
     }
 
+    /** als-ms evaluation MSE.java:122-160: {mse, ratings scored}. */
+    public double[] alsMse(ByteBuffer u, ByteBuffer i, ByteBuffer rating, long n) { return alsMse(ctx, u, i, rating, n); }
+
+    /** One micro-batch of the als-ms online SGD (SGD.java:160-217); outUser / outItem receive n x rank doubles. */
+    public void alsSgdStep(ByteBuffer user, ByteBuffer item, ByteBuffer rating, long n, double learningRate, double userReg,
+                           double itemReg, ByteBuffer userMean, ByteBuffer itemMean, boolean apply, ByteBuffer outUser, ByteBuffer outItem) {
+        alsSgdStep(ctx, user, item, rating, n, learningRate, userReg, itemReg, userMean, itemMean, apply, outUser, outItem);
+    }
+
+    /** env.readCsvFile[(Int, Int, Double)] on the GPU (ALSImpl.scala:29-32); pass null outputs to size them. Returns rows. */
+    public long parseRatingsCsv(ByteBuffer text, long nbytes, char delimiter, boolean ignoreFirstLine, ByteBuffer user, ByteBuffer item,
+                                ByteBuffer rating, long capacity) {
+        return parseRatingsCsv(ctx, text, nbytes, (byte) delimiter, ignoreFirstLine, user, item, rating, capacity);
+    }
+
+    /** env.readLibSVM on the GPU (SVMImpl.scala:21); pass null outputs to size them. Returns {rows, nnz, dim}. */
+    public long[] parseLibSvm(ByteBuffer text, long nbytes, ByteBuffer label, long rowCapacity, ByteBuffer csrPtr, ByteBuffer csrIdx,
+                              ByteBuffer csrVal, long nnzCapacity) {
+        return parseLibSvm(ctx, text, nbytes, label, rowCapacity, csrPtr, csrIdx, csrVal, nnzCapacity);
+    }
+
     private static native long create(int device);
     private static native void destroy(long ctx);
     private static native long[] alsFit(long ctx, ByteBuffer user, ByteBuffer item, ByteBuffer rating, long nnz, int rank,
@@ -51,6 +72,14 @@ public final class Native implements AutoCloseable {
     private static native void alsSetModel(long ctx, ByteBuffer userIds, ByteBuffer userFactors, long nUsers, ByteBuffer itemIds,
                                            ByteBuffer itemFactors, long nItems, int rank);
     private static native void alsPredict(long ctx, ByteBuffer u, ByteBuffer i, long n, ByteBuffer out, ByteBuffer found);
+    private static native double[] alsMse(long ctx, ByteBuffer u, ByteBuffer i, ByteBuffer rating, long n);
+    private static native void alsSgdStep(long ctx, ByteBuffer user, ByteBuffer item, ByteBuffer rating, long n, double learningRate,
+                                          double userReg, double itemReg, ByteBuffer userMean, ByteBuffer itemMean, boolean apply,
+                                          ByteBuffer outUser, ByteBuffer outItem);
+    private static native long parseRatingsCsv(long ctx, ByteBuffer text, long nbytes, byte delimiter, boolean ignoreFirstLine,
+                                               ByteBuffer user, ByteBuffer item, ByteBuffer rating, long capacity);
+    private static native long[] parseLibSvm(long ctx, ByteBuffer text, long nbytes, ByteBuffer label, long rowCapacity,
+                                             ByteBuffer csrPtr, ByteBuffer csrIdx, ByteBuffer csrVal, long nnzCapacity);
     private static native void svmFit(long ctx, ByteBuffer x, int xDtype, ByteBuffer csrPtr, ByteBuffer csrIdx, ByteBuffer y,
                                       long n, int dim, ByteBuffer blockId, int blocks, int iterations, long localIterations,
                                       double regularization, double stepsize, long seed, int rngMode, ByteBuffer w);
