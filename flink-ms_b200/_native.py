@@ -18,7 +18,7 @@ ERR_INVALID_ARG, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_OOM = -1, -2, -3, -4,
 X_DENSE_F32, X_DENSE_F64, X_CSR_F64 = 0, 1, 2
 RNG_PER_BLOCK, RNG_SHARED_SUBTASK = 0, 1
 USERS, ITEMS = 0, 1
-ALS_KERNEL_AUTO, ALS_KERNEL_GENERIC, ALS_KERNEL_TC = 0, 1, 2
+ALS_KERNEL_AUTO, ALS_KERNEL_GENERIC, ALS_KERNEL_TC, ALS_KERNEL_TC_TMA, ALS_KERNEL_TC_LDGSTS = 0, 1, 2, 3, 4
 SVM_KERNEL_AUTO, SVM_KERNEL_GENERIC, SVM_KERNEL_WARP = 0, 1, 2
 
 _vp = C.c_void_p

@@ -121,6 +121,12 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // TMA gather4: four rows (row indices r0..r3, 64 halves each) of a 2-D fp16 tensor -> 512 contiguous swizzled bytes.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 // Issues the hi-plane and lo-plane gathers of one row quartet from ONE elected lane (the operands must be valid in
 // every lane: they come from warp shuffles), predicated instead of branched so the compiler emits no lane loop.
 __device__ __forceinline__ void tma_gather4_pair(uint32_t dst_hi, uint32_t dst_lo, const CUtensorMap *map, uint32_t bar, int r0, int r1,
@@ -403,12 +409,13 @@ __device__ __forceinline__ void solver_trsm_syrk(float2 (&A)[16], float &b1, flo
     }
 }
 
-template <bool DUMP>
+template <bool DUMP, bool LDGSTS>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
     const __grid_constant__ CUtensorMap map_pl, const int64_t *__restrict__ ptr,
     const int32_t *__restrict__ stage_ptr, const int32_t *__restrict__ colp, const float *__restrict__ valp,
     const int32_t *__restrict__ cta_rows, float *__restrict__ T, __half *__restrict__ T_pl, float lambda,
-    int64_t row_begin, int *__restrict__ info, float *__restrict__ dump, __half *const *__restrict__ peers, int n_peers) {
+    int64_t row_begin, int *__restrict__ info, float *__restrict__ dump, __half *const *__restrict__ peers, int n_peers,
+    const __half *__restrict__ S_pl) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
     const uint32_t sm_base = smem_u32(sm);
@@ -425,7 +432,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
     // zero the ring once: the R / R' chunks only ever get their first four bytes per row rewritten
     for (int i = threadIdx.x; i < NSTG * STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(sm + Smem::ring)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTG; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        // arrivals per full barrier: one expect_tx arrive (TMA gathers) or, with LDGSTS producers, every lane's copies
+        // (cp.async.mbarrier.arrive.noinc) plus one release-arrive for the rating chunks
+        for (int s = 0; s < NSTG; ++s) { mbar_init(bar_full(s), LDGSTS ? 33 : 1); mbar_init(bar_empty(s), 1); }
         for (int a = 0; a < NACC; ++a) { mbar_init(bar_acc_full(a), 1); mbar_init(bar_acc_empty(a), N_EPI); }
         for (int g = 0; g < NGB; ++g) { mbar_init(bar_g_full(g), N_EPI); mbar_init(bar_g_empty(g), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -464,29 +473,62 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             if (c + 2 * N_PROD < n_local) { idx2 = cp[(int64_t)(c + 2 * N_PROD) * KROWS]; rt2 = vp[(int64_t)(c + 2 * N_PROD) * KROWS]; }
             const int slot = c % NSTG;
             const uint32_t stage = sm_base + Smem::ring + slot * STAGE_BYTES;
-            // every lane gets the 16 row indices of the stage (lanes 0..15 hold one each)
-            int r[16];
+            if (LDGSTS) {
+                // Short rows (a handful of stages per system): the gathered plane rows sit in L2 and the producers' own
+                // instruction stream competes with the solver warps, so 16-byte asynchronous copies (LDGSTS: 8 per lane
+                // and stage, a quarter of the instructions of the elected-lane TMA issue) are used instead.  Lane l moves
+                // chunk (l & 7) of rows (l >> 3) + 4 k of both halves of the plane row into the 128B-swizzled tile
+                // layout (chunk j of row r at j ^ (r & 7)); the MMA issuer adds the generic -> async proxy fence.
+                const int rq = lane >> 3, jc = lane & 7;
+                int ri[4];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = __shfl_sync(0xffffffffu, idx0, i);
-            mbar_wait(bar_empty(slot), ((c / NSTG) & 1) ^ 1);
-            // ratings: R row r = (r_hi, r_lo * 2^11, 0...), R' row r = (0, r_hi, 0...); 16-byte chunk 0 sits at chunk (r & 7)
-            if (lane < 16) {
-                __half rh, rl;
-                split_half(rt0, rh, rl);
-                const uint32_t off = (uint32_t)lane * 128u + (((uint32_t)lane & 7u) << 4);
-                const uint32_t w0 = (uint32_t)__half_as_ushort(rh) | ((uint32_t)__half_as_ushort(rl) << 16);
-                const uint32_t w1 = (uint32_t)__half_as_ushort(rh) << 16;
-                *reinterpret_cast<uint32_t *>(sm + Smem::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + off) = w0;
-                *reinterpret_cast<uint32_t *>(sm + Smem::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + (off ^ 16u)) = w1;   // logical column group 1
+                for (int k = 0; k < 4; ++k) ri[k] = __shfl_sync(0xffffffffu, idx0, 4 * k + rq);
+                mbar_wait(bar_empty(slot), ((c / NSTG) & 1) ^ 1);
+                if (lane < 16) {
+                    __half rh, rl;
+                    split_half(rt0, rh, rl);
+                    const uint32_t off = (uint32_t)lane * 128u + (((uint32_t)lane & 7u) << 4);
+                    const uint32_t w0 = (uint32_t)__half_as_ushort(rh) | ((uint32_t)__half_as_ushort(rl) << 16);
+                    const uint32_t w1 = (uint32_t)__half_as_ushort(rh) << 16;
+                    *reinterpret_cast<uint32_t *>(sm + Smem::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + off) = w0;
+                    *reinterpret_cast<uint32_t *>(sm + Smem::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + (off ^ 16u)) = w1;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int r = 4 * k + rq;
+                    const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((jc ^ (r & 7)) << 4);
+                    const char *src = reinterpret_cast<const char *>(S_pl) + (size_t)ri[k] * (PLANE_PITCH * 2) + (size_t)jc * 16;
+                    cp_async16(dst, src);
+                    cp_async16(dst + TILE_BYTES, src + D * 2);
+                }
+                cp_async_arrive_noinc(bar_full(slot));             // fires when this lane's eight copies have landed
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full(slot));        // releases the rating chunks written above
+            } else {
+                // every lane gets the 16 row indices of the stage (lanes 0..15 hold one each)
+                int r[16];
+    #pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = __shfl_sync(0xffffffffu, idx0, i);
+                mbar_wait(bar_empty(slot), ((c / NSTG) & 1) ^ 1);
+                // ratings: R row r = (r_hi, r_lo * 2^11, 0...), R' row r = (0, r_hi, 0...); 16-byte chunk 0 sits at chunk (r & 7)
+                if (lane < 16) {
+                    __half rh, rl;
+                    split_half(rt0, rh, rl);
+                    const uint32_t off = (uint32_t)lane * 128u + (((uint32_t)lane & 7u) << 4);
+                    const uint32_t w0 = (uint32_t)__half_as_ushort(rh) | ((uint32_t)__half_as_ushort(rl) << 16);
+                    const uint32_t w1 = (uint32_t)__half_as_ushort(rh) << 16;
+                    *reinterpret_cast<uint32_t *>(sm + Smem::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + off) = w0;
+                    *reinterpret_cast<uint32_t *>(sm + Smem::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + (off ^ 16u)) = w1;   // logical column group 1
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_expect_tx(bar_full(slot), 2 * TILE_BYTES);
+                __syncwarp();
+    #pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    tma_gather4_pair(stage + t * 512, stage + TILE_BYTES + t * 512, &map_pl, bar_full(slot), r[4 * t], r[4 * t + 1],
+                                     r[4 * t + 2], r[4 * t + 3]);
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_expect_tx(bar_full(slot), 2 * TILE_BYTES);
-            __syncwarp();
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                tma_gather4_pair(stage + t * 512, stage + TILE_BYTES + t * 512, &map_pl, bar_full(slot), r[4 * t], r[4 * t + 1],
-                                 r[4 * t + 2], r[4 * t + 3]);
             idx0 = idx1; rt0 = rt1;
             idx1 = idx2; rt1 = rt2;
         }
@@ -511,6 +553,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
             for (int st = 0; st < nst; ++st) {
                 if (!ready) mbar_wait(bar0 + 8u * slot, ph);
                 tc_fence_after();
+                if (LDGSTS) fence_proxy_async();                   // generic-proxy writes (cp.async, st.shared) -> tensor-core reads
                 uint32_t nslot = slot + 1, nph = ph, nenc = enc + (STAGE_BYTES >> 4);
                 if (nslot == NSTG) { nslot = 0; nph ^= 1u; nenc = enc0; }
                 const uint32_t nready = mbar_test(bar0 + 8u * nslot, nph);
@@ -837,19 +880,21 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
     const int64_t rows = re - rb;
     const int grid = (int)(rows < ctx->sm_count ? rows : ctx->sm_count);
     FMS_TRY(ensure_stage_csr(ctx, which, rb, re, zero_row, grid));
-    if (dump) {
-        FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::k_als_rows_tc64<true><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_pl, A.ptr[which].p, A.stage_ptr[which].p,
-                                                                                 A.colp[which].p, A.valp[which].p, A.cta_rows[which].p,
-                                                                                 A.fac[which].p, t_hi, lambda, rb,
-                                                                                 A.info.p, dump, peers, n_peers);
-    } else {
-        FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::k_als_rows_tc64<false><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(m_pl, A.ptr[which].p, A.stage_ptr[which].p,
-                                                                                  A.colp[which].p, A.valp[which].p, A.cta_rows[which].p,
-                                                                                  A.fac[which].p, t_hi, lambda, rb,
-                                                                                  A.info.p, nullptr, peers, n_peers);
-    }
+    // producer flavour: LDGSTS for short rows (see the kernel), TMA gather4 for long ones
+    const int64_t n_side = which == 0 ? A.n_users : A.n_items;
+    const bool ldgsts = !dump && (A.kernel == FMS_ALS_KERNEL_TC_LDGSTS ||
+                                  (A.kernel != FMS_ALS_KERNEL_TC_TMA && n_side > 0 && A.nnz / n_side < 16 * tc::KROWS));
+#define FMS_TC_LAUNCH(DUMPF, LDG, DUMP_PTR)                                                                                          \
+    do {                                                                                                                             \
+        FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<DUMPF, LDG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        tc::k_als_rows_tc64<DUMPF, LDG><<<grid, tc::NWARPS * 32, smem, ctx->stream>>>(                                                \
+            m_pl, A.ptr[which].p, A.stage_ptr[which].p, A.colp[which].p, A.valp[which].p, A.cta_rows[which].p, A.fac[which].p, t_hi,  \
+            lambda, rb, A.info.p, DUMP_PTR, peers, n_peers, p_hi);                                                                   \
+    } while (0)
+    if (dump) FMS_TC_LAUNCH(true, false, dump);
+    else if (ldgsts) FMS_TC_LAUNCH(false, true, nullptr);
+    else FMS_TC_LAUNCH(false, false, nullptr);
+#undef FMS_TC_LAUNCH
     FMS_LAUNCH_CHECK(ctx);
     // the kernel wrote the planes of its own rows; with one shard that is the whole side
     A.plane_valid[which] = (A.shard_count == 1);

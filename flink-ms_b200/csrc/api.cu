@@ -128,7 +128,7 @@ FMS_API int fms_als_init(fms_ctx *ctx, int rank, int64_t seed) {
 
 FMS_API int fms_als_set_kernel(fms_ctx *ctx, int kernel) {
     if (!ctx) return FMS_ERR_INVALID_ARG;
-    if (kernel < FMS_ALS_KERNEL_AUTO || kernel > FMS_ALS_KERNEL_TC) return fail(ctx, FMS_ERR_INVALID_ARG, "bad ALS kernel id %d", kernel);
+    if (kernel < FMS_ALS_KERNEL_AUTO || kernel > FMS_ALS_KERNEL_TC_LDGSTS) return fail(ctx, FMS_ERR_INVALID_ARG, "bad ALS kernel id %d", kernel);
     ctx->als.kernel = kernel;
     return FMS_OK;
 }
@@ -147,7 +147,7 @@ static int als_half_step_rows(fms_ctx *ctx, int which, double lambda, int chunk,
     if (chunk == 0) FMS_CUDA(ctx, cudaMemsetAsync(A.info.p, 0, sizeof(int), ctx->stream));
     bool tc = false;
     if (A.kernel != FMS_ALS_KERNEL_GENERIC) tc = als_tc_supported(ctx, A.rank) != 0;
-    if (A.kernel == FMS_ALS_KERNEL_TC && !tc) return fail(ctx, FMS_ERR_UNSUPPORTED, "tensor-core ALS kernel does not cover rank %d", A.rank);
+    if (A.kernel >= FMS_ALS_KERNEL_TC && !tc) return fail(ctx, FMS_ERR_UNSUPPORTED, "tensor-core ALS kernel does not cover rank %d", A.rank);
     A.fac64_valid = false;
     A.plane_valid[which] = false;                      // the tensor-core kernel re-validates the planes it writes itself
     if (tc) FMS_TRY(als_launch_half_step_tc(ctx, which, (float)lambda, rb, re));

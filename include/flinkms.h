@@ -53,7 +53,9 @@ enum { FMS_RNG_PER_BLOCK = 0, FMS_RNG_SHARED_SUBTASK = 1 };
 /* which factor matrix */
 enum { FMS_USERS = 0, FMS_ITEMS = 1 };
 /* ALS solver selection: AUTO picks the tensor-core kernel when the rank supports it */
-enum { FMS_ALS_KERNEL_AUTO = 0, FMS_ALS_KERNEL_GENERIC = 1, FMS_ALS_KERNEL_TC = 2 };
+/* TC = tensor-core kernel, producer flavour chosen per half-step (TMA gather4 for long rows, 16-byte LDGSTS copies for
+ * short ones); TC_TMA / TC_LDGSTS force one flavour (tests, experiments). */
+enum { FMS_ALS_KERNEL_AUTO = 0, FMS_ALS_KERNEL_GENERIC = 1, FMS_ALS_KERNEL_TC = 2, FMS_ALS_KERNEL_TC_TMA = 3, FMS_ALS_KERNEL_TC_LDGSTS = 4 };
 /* SVM sweep selection */
 enum { FMS_SVM_KERNEL_AUTO = 0, FMS_SVM_KERNEL_GENERIC = 1, FMS_SVM_KERNEL_WARP = 2 };
 

@@ -272,6 +272,20 @@ def test_tensor_core_and_generic_kernels_agree_over_iterations(fms, ctx):
     assert rel_err(out["tc"][0], out["generic"][0]) <= 5e-5 and rel_err(out["tc"][1], out["generic"][1]) <= 5e-5
 
 
+def test_tensor_core_producer_flavours_are_bitwise_equal(fms, ctx):
+    """The two producer flavours of the tensor-core kernel (TMA gather4 / 16-byte LDGSTS copies) feed the same bytes to the
+    same MMAs: factors must be bitwise equal, whatever the automatic per-half-step choice picks."""
+    u, i, r = _case(fms, 2000, 60, 70_000, seed=13)          # users: ~35 ratings per row, items: ~1170 per row
+    out = {}
+    for name, k in (("auto", fms._native.ALS_KERNEL_TC), ("tma", fms._native.ALS_KERNEL_TC_TMA), ("ldgsts", fms._native.ALS_KERNEL_TC_LDGSTS)):
+        ctx.als_set_kernel(k)
+        ctx.als_fit(u, i, r, 64, 3, 0.9, 42)
+        out[name] = (ctx.als_get_factors(0)[1], ctx.als_get_factors(1)[1])
+    ctx.als_set_kernel(fms._native.ALS_KERNEL_AUTO)
+    for name in ("tma", "ldgsts"):
+        assert np.array_equal(out[name][0], out["auto"][0]) and np.array_equal(out[name][1], out["auto"][1])
+
+
 @pytest.mark.parametrize("rank", [8, 64])
 def test_chunked_half_step_equals_full(fms, ctx, rank):
     """fms_als_half_step_chunk over all chunks == one fms_als_half_step (the pipelined exchange of dist.py relies on it)."""
