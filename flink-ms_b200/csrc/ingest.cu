@@ -43,8 +43,9 @@ __device__ bool eisel_lemire(uint64_t w, int q, double *out) {
     exp2 -= 1 ^ msb;
     // exact half-way case (round bit set, nothing below): decidable only where the product is exact (5^|q| fits the
     // table entry, q in [-4, 23]) -- then round to even, i.e. do not round up; elsewhere the 128 bits cannot tell
-    const bool tie = x_lo == 0 && (x_hi & 0x1FF) == 0 && (mant & 3) == 1;
-    if (tie && (q < -4 || q > 23)) return false;
+    const bool maybe_tie = x_lo == 0 && (x_hi & 0x1FF) == 0 && (mant & 3) == 1;
+    if (maybe_tie && (q < -4 || q > 23)) return false;
+    const bool tie = maybe_tie && (x_hi & ((1ull << (msb + 9)) - 1)) == 0;    // every bit below the round bit is zero
     if (!tie) mant += mant & 1;
     mant >>= 1;
     if (mant >> 53) { mant >>= 1; exp2 += 1; }

@@ -2,6 +2,7 @@
 ALSImpl.scala:84, SVMImpl.scala:35/:42-45/:63-71, ALSMeanVector.scala:28-35, ALSKafkaConsumer.java:78-92,
 QueryClientHelper.java:105-139."""
 import importlib
+import os
 
 import numpy as np
 import pytest
@@ -82,3 +83,72 @@ def test_queryable_state_client_schema():
     c.close()
     with pytest.raises(RuntimeError):
         c.queryState("SVM_MODEL", "1")
+
+
+def _pow10_table():
+    import re
+    path = os.path.join(os.path.dirname(__file__), "..", "flink-ms_b200", "csrc", "pow10_table.cuh")
+    rows = re.findall(r"\{0x([0-9a-f]{16})ULL, 0x([0-9a-f]{16})ULL\}", open(path).read())
+    assert len(rows) == 651
+    return [(int(h, 16), int(l, 16)) for h, l in rows]
+
+
+def _eisel_lemire(w, q, table):
+    """Python transcription of csrc/ingest.cu::eisel_lemire (same table, same steps) -- pins the generated table and the
+    algorithm on the CPU; the device code itself is checked bit-exactly in tests/test_ingest_gpu.py."""
+    import struct
+    M = (1 << 64) - 1
+    if w == 0:
+        return 0.0
+    if q < -342 or q > 308:
+        return None
+    lz = 64 - w.bit_length()
+    w <<= lz
+    exp2 = (((217706 * q) >> 16) + 64 + 1023) - lz
+    t_hi, t_lo = table[q + 342]
+    x = w * t_hi
+    x_hi, x_lo = x >> 64, x & M
+    if (x_hi & 0x1FF) == 0x1FF and ((x_lo + w) & M) < w:
+        y = w * t_lo
+        y_hi, y_lo = y >> 64, y & M
+        m_hi, m_lo = x_hi, (x_lo + y_hi) & M
+        if m_lo < x_lo:
+            m_hi += 1
+        if (m_hi & 0x1FF) == 0x1FF and ((m_lo + 1) & M) == 0 and ((y_lo + w) & M) < w:
+            return None
+        x_hi, x_lo = m_hi, m_lo
+    msb = x_hi >> 63
+    mant = x_hi >> (msb + 9)
+    exp2 -= 1 ^ msb
+    maybe_tie = x_lo == 0 and (x_hi & 0x1FF) == 0 and (mant & 3) == 1
+    if maybe_tie and (q < -4 or q > 23):
+        return None
+    tie = maybe_tie and (x_hi & ((1 << (msb + 9)) - 1)) == 0
+    if not tie:
+        mant += mant & 1
+    mant >>= 1
+    if mant >> 53:
+        mant >>= 1
+        exp2 += 1
+    if not (1 <= exp2 <= 0x7FE):
+        return None
+    return struct.unpack("<d", struct.pack("<Q", (exp2 << 52) | (mant & 0x000FFFFFFFFFFFFF)))[0]
+
+
+def test_eisel_lemire_table_and_algorithm_match_python_float():
+    table = _pow10_table()
+    rng = np.random.default_rng(11)
+    undecided = 0
+    for it in range(40000):
+        digits = int(rng.integers(1, 20))
+        w = int(rng.integers(1, 10 ** digits)) if digits < 19 else int(rng.integers(10 ** 18, 2 ** 63))
+        q = int(rng.integers(-300, 290)) if it % 2 else int(rng.integers(-6, 26))   # half of them where ties are decidable
+        got = _eisel_lemire(w, q, table)
+        if got is None:
+            undecided += 1
+            continue
+        assert got == float(f"{w}e{q}"), (w, q)
+    assert undecided < 400                                                     # the fallback-free parser rejects only rare cases
+    assert _eisel_lemire(9007199254740993, 0, table) == 9007199254740992.0     # exact tie -> even
+    assert _eisel_lemire(9007199254740995, 0, table) == 9007199254740996.0
+    assert _eisel_lemire(17976931348623157, 292, table) == 1.7976931348623157e308

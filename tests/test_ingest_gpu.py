@@ -18,7 +18,10 @@ def _literals(rng, n):
         elif kind == 2:
             out.append(str(int(rng.integers(0, 6))))                          # integer literal
         elif kind == 3:
-            out.append("%.6e" % float(rng.standard_normal() * 10.0 ** int(rng.integers(-200, 200))))
+            if k % 16 == 3:                                                       # integers times small powers of ten: exact products, ties decidable
+                out.append("%de%d" % (int(rng.integers(1, 2 ** 62)), int(rng.integers(-6, 26))))
+            else:
+                out.append("%.6e" % float(rng.standard_normal() * 10.0 ** int(rng.integers(-200, 200))))
         elif kind == 4:
             out.append(("-" if rng.random() < 0.5 else "+") + "%.12f" % rng.uniform(0, 1e6))
         elif kind == 5:
@@ -27,7 +30,7 @@ def _literals(rng, n):
             out.append("%d.%017d" % (int(rng.integers(1, 100)), int(rng.integers(0, 10 ** 17))))    # 18-19 significant digits
         else:
             out.append(["0", "0.0", ".5", "5.", "1e3", "1E-3", "2.5e+10", "NaN", "Infinity", "-Infinity", "1.0d", "3f", "0.30000000000000004",
-                        "9007199254740993", "0.1000000000000000055511151231257827021181583404541015625", "1.7976931348623157e308", "2.2250738585072014e-308", "123456789012345678"][k // 8 % 18])
+                        "9007199254740993", "293710372636606e3", "0.1000000000000000055511151231257827021181583404541015625", "1.7976931348623157e308", "2.2250738585072014e-308", "123456789012345678"][k // 8 % 19])
     return out
 
 
