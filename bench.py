@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--cpu-nnz", type=int, default=10_000_000)
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--als-kernel", type=int, default=0)
-    ap.add_argument("--als-chunks", type=int, default=4, help="N>1, without --als-p2p 1: solve each shard in this many chunks, all-gather overlapped")
+    ap.add_argument("--als-chunks", type=int, default=1, help="N>1, without --als-p2p 1: solve each shard in this many chunks, all-gather overlapped")
     ap.add_argument("--als-p2p", type=int, default=1, help="N>1: the kernel stores plane rows into all replicas over NVLink (CUDA IPC)")
     ap.add_argument("--svm-kernel", type=int, default=0)
     args = ap.parse_args()

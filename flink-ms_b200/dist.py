@@ -4,7 +4,8 @@ ALS: every rank holds the full CSR pair and full factor r
 [g*S, (g+1)*S) of the side being updated, then the shards are ALL-GATHERED into every replica -- the exchange
 Flink does with a join + coGroup network shuffle between half-steps (Appendix A.1 `updateFactors` message
 build).  Per-row arithmetic is identical to the 1-GPU run, so results are bitwise equal.  On GPUs the shard is
-solved in up to `max_chunks` chunks and chunk k's all-gather runs on a second stream under the solve of chunk k+1;
+solved in up to `max_chunks` chunks (default 1: measured slower than the plain all-gather at 2 GPUs because the persistent
+solver kernel owns every SM, so the NCCL kernel cannot really run beside it) with chunk k's all-gather on a second stream;
 or -- `ContextALSBackend.enable_p2p` -- the kernel itself stores each solved row into every rank's replica over NVLink
 (CUDA IPC mappings), and only a barrier follows the half-step.
 
@@ -123,7 +124,7 @@ class ContextALSBackend:
 class DistributedALS:
     """iterate(T){ users = f(items); items = f(users) }; users = f(items), sharded by rows."""
 
-    def __init__(self, backend, rank_dim: int, group=None, max_chunks: int = 4, min_chunk_rows: int = 1024):
+    def __init__(self, backend, rank_dim: int, group=None, max_chunks: int = 1, min_chunk_rows: int = 1024):
         self.b = backend
         self.rank_dim = rank_dim
         self.group = group
