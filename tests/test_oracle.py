@@ -213,3 +213,26 @@ def test_sgd_restatement_properties():
     assert np.allclose(ou[1], um + 0.1 * e9 * I[0])                               # cold start from the mean row
     with pytest.raises(ValueError):
         npr.sgd_step(uid, U, iid, I, [1], [2], [5.0], 0.1, 0.0, 0.0, None, im)
+
+
+def test_als_half_step_matches_lapack_dposv():
+    """FlinkML solves every row with netlib LAPACK `dposv("U", ...)` on the upper triangle of X^T X + lambda n I (SURVEY.md
+    Appendix A.1).  The same routine is reachable here through scipy: the oracle's rows must agree with it to a few ulps
+    (identical algorithm, possibly different blocking inside the BLAS)."""
+    scipy_lapack = pytest.importorskip("scipy.linalg.lapack")
+    synth = __import__("importlib").import_module("flink-ms_b200.synth")
+    u, i, r = synth.als_ratings(120, 40, 1500, seed=31)
+    for rank in (4, 16, 64):
+        orc = oracle.OracleALS(u, i, r)
+        orc.init(rank, 7)
+        ids_i, Y = orc.factors(1)
+        orc.half_step(0, 0.3)
+        ids_u, X = orc.factors(0)
+        for row in range(0, orc.n_users, 7):
+            sel = u == ids_u[row]
+            V = Y[np.searchsorted(ids_i, i[sel])]
+            A = V.T @ V + 0.3 * sel.sum() * np.eye(rank)
+            b = V.T @ r[sel]
+            _, x, info = scipy_lapack.dposv(A, b.reshape(-1, 1), lower=0)
+            assert info == 0
+            assert np.abs(x[:, 0] - X[row]).max() <= 1e-11 * max(1.0, np.abs(X[row]).max())
