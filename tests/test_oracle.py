@@ -236,3 +236,21 @@ def test_als_half_step_matches_lapack_dposv():
             _, x, info = scipy_lapack.dposv(A, b.reshape(-1, 1), lower=0)
             assert info == 0
             assert np.abs(x[:, 0] - X[row]).max() <= 1e-11 * max(1.0, np.abs(X[row]).max())
+
+
+def test_svm_converges_to_the_hinge_svm_optimum_of_liblinear():
+    """Run long enough with one block, CoCoA/SDCA reaches the optimum of  lambda/2 |w|^2 + 1/n sum hinge(y w.x)  -- the
+    objective FlinkML states for its SVM.  liblinear (through scikit-learn, C = 1 / (lambda n), hinge loss, no
+    intercept) solves the same problem with an unrelated implementation: primal objectives must agree to 1e-3."""
+    sk = pytest.importorskip("sklearn.svm")
+    synth = __import__("importlib").import_module("flink-ms_b200.synth")
+    X, y, _ = synth.svm_data(400, 12, seed=17)
+    X = np.asarray(X, np.float64); y = np.asarray(y, np.float64)
+    lam = 0.05
+    w, alpha = oracle.svm_fit(X, y, np.zeros(len(y), np.int32), 1, 60, len(y), regularization=lam, stepsize=1.0, seed=5, return_alpha=True)
+    primal, dual = oracle.svm_objectives(X, y, w, alpha, lam)
+    assert primal - dual <= 5e-4 * max(1.0, abs(primal))                     # duality gap: converged
+    ref = sk.LinearSVC(loss="hinge", C=1.0 / (lam * len(y)), fit_intercept=False, dual=True, tol=1e-10, max_iter=200000).fit(X, y)
+    wr = ref.coef_.ravel()
+    pr = 0.5 * lam * float(wr @ wr) + float(np.maximum(0.0, 1.0 - y * (X @ wr)).mean())
+    assert abs(primal - pr) <= 1e-3 * max(1.0, abs(pr))
