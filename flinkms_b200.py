@@ -8,3 +8,6 @@ if _root not in sys.path:
     sys.path.insert(0, _root)
 _pkg = importlib.import_module("flink-ms_b200")
 sys.modules[__name__] = _pkg
+
+if __name__ == "__main__":                      # python flinkms_b200.py als|svm ...  (or python -m flinkms_b200 als|svm ...)
+    sys.exit(importlib.import_module("flink-ms_b200.jobs").main())
