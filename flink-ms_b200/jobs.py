@@ -163,6 +163,54 @@ def svm_impl(argv, ctx: N.Context | None = None, out=sys.stdout):
             ctx.close()
 
 
+def als_predict_console(lines, client, out=sys.stdout):
+    """The query loop of flink-queryable-client/.../qs/ALSPredict.java:58-92 over a `formats.QueryableStateClient`: one
+    `user,item` pair per line -> two state lookups ("<user>-U", "<item>-I"), the dot product of the parsed factor strings."""
+    print("Enter <User,Item> to predict.", file=out)
+    for line in lines:
+        key = line.upper().strip()
+        out.write("[info] Querying the model for <user,item> pair '%s'\n" % key)
+        try:
+            tokens = key.split(",")
+            user_t = client.queryState("ALS_MODEL", tokens[0] + "-U")
+            item_t = client.queryState("ALS_MODEL", tokens[1] + "-I")
+            if user_t is not None and item_t is not None:
+                uf = [float(t) for t in user_t[1].split(";")]
+                itf = [float(t) for t in item_t[1].split(";")]
+                if len(uf) != len(itf):
+                    raise ValueError("DimensionMismatchException: %d != %d" % (len(itf), len(uf)))
+                prediction = 0.0
+                for a, b in zip(uf, itf):                                           # ArrayRealVector.dotProduct: sequential
+                    prediction += a * b
+                out.write("ALS Prediction =  %f \n" % prediction)
+            else:
+                out.write("User or Item Factors do not exist in the model for the query: ")   # sic: no newline, key dropped by printf
+        except Exception as e:  # noqa: BLE001  (the reference catches Exception and prints the stack trace)
+            out.write("Query failed because of the following Exception:\n%s: %s\n" % (type(e).__name__, e))
+
+
+def svm_predict_console(lines, client, outputDecisionFunction=False, thresholdValue=0.0, out=sys.stdout):
+    """The query loop of flink-queryable-client/.../qs/SVMPredict.java:58-90: one sparse vector `id:val id:val ...` per line,
+    one state lookup per feature id, raw value = sum of weight * value, strict `>` against the threshold."""
+    print("Enter Vector data to predict.", file=out)
+    for line in lines:
+        out.write("[info] Querying the model for vector '%s' \n" % line)
+        try:
+            raw = 0.0
+            for tok in line.strip().split(" "):
+                pair = tok.split(":")
+                fid, val = pair[0], float(pair[1])
+                model_val = client.queryState("SVM_MODEL", fid)
+                if model_val is not None:
+                    raw += float(model_val[1]) * val
+                else:
+                    out.write("Could not find the value for feature ID: %s \n" % fid)
+            prediction = raw if outputDecisionFunction else (1.0 if raw > thresholdValue else -1.0)
+            out.write("SVM Prediction =  %f \n" % prediction)
+        except Exception as e:  # noqa: BLE001
+            out.write("Query failed because of the following Exception:\n%s: %s\n" % (type(e).__name__, e))
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv or argv[0] not in ("als", "svm"):

@@ -75,3 +75,30 @@ def test_svm_job_end_to_end(fms, ctx, tmp_path):
     assert lines[0].startswith("Printing result to stdout.") and lines[1].startswith("0,1:") and lines[2].startswith("1,4:")
     with pytest.raises(RuntimeError):
         jobs.svm_impl(["--blocks", "3"], ctx=ctx)
+
+
+def test_predict_consoles_follow_the_reference_clients():
+    """ALSPredict.java:58-92 / SVMPredict.java:58-90 over the host-side QueryableStateClient (no GPU involved)."""
+    client = formats.QueryableStateClient(None)
+    U = np.array([[0.5, -1.25, 2.0], [1.0, 0.0, 3.0]]); I = np.array([[2.0, 4.0, -0.5]])
+    client.load_als([7, 9], U, [3], I)
+    out = io.StringIO()
+    jobs.als_predict_console(["7,3\n", " 9,3 ", "8,3", "7", "x,y"], client, out)
+    text = out.getvalue()
+    assert text.startswith("Enter <User,Item> to predict.\n[info] Querying the model for <user,item> pair '7,3'\n")
+    assert "ALS Prediction =  %f \n" % (0.5 * 2.0 + -1.25 * 4.0 + 2.0 * -0.5) in text
+    assert "ALS Prediction =  %f \n" % (1.0 * 2.0 + 3.0 * -0.5) in text
+    assert text.count("User or Item Factors do not exist in the model for the query: ") == 2       # unknown user 8, non-numeric ids
+    assert text.count("Query failed because of the following Exception:") == 1                   # "7": tokens[1] missing
+    w = np.array([0.25, -1.0, 0.0, 2.0])
+    client.load_svm(w)
+    out = io.StringIO()
+    jobs.svm_predict_console(["1:2.0 4:0.5", "2:1.0", "1:1.0 9:3.0", "1:0.0", "bad"], client, False, 0.0, out)
+    lines = out.getvalue().splitlines()
+    assert lines[0] == "Enter Vector data to predict."
+    preds = [l for l in lines if l.startswith("SVM Prediction")]
+    assert preds == ["SVM Prediction =  1.000000 ", "SVM Prediction =  -1.000000 ", "SVM Prediction =  1.000000 ", "SVM Prediction =  -1.000000 "]
+    assert "Could not find the value for feature ID: 9 " in lines and out.getvalue().count("Query failed") == 1
+    out = io.StringIO()
+    jobs.svm_predict_console(["1:2.0 4:0.5"], client, True, 0.0, out)
+    assert "SVM Prediction =  %f " % (0.25 * 2.0 + 2.0 * 0.5) in out.getvalue()
