@@ -163,6 +163,30 @@ def svm_impl(argv, ctx: N.Context | None = None, out=sys.stdout):
             ctx.close()
 
 
+def als_mean_vector(argv, out=sys.stdout):
+    """ALSMeanVector.main(args) (flink-als/.../ALSMeanVector.scala:12-48): the mean of the factor rows of an ALS output file as
+    a `MEAN,U|I,m1;m2;...` row (the cold-start fallback of the online SGD job).  Host arithmetic, like the reference:
+    a left-to-right fp64 sum divided by the row count."""
+    params = ParameterTool.fromArgs(argv)
+    t = params.getRequired("type")
+    if t == "item":
+        factor_type = "I"
+    elif t == "user":
+        factor_type = "U"
+    else:
+        raise ValueError("specify type as either 'item' or 'user'.")                 # IllegalArgumentException
+    from .formats import als_mean_row
+    with open(params.get("input")) as f:
+        vectors = [[float(v) for v in row.rstrip("\n").split(",")[2].split(";")] for row in f if row.strip()]
+    row = als_mean_row(np.array(vectors, np.float64), factor_type)
+    if params.has("output"):
+        _write_text(params.get("output"), [row])
+    else:
+        print("Printing results to stdout. Use --output to specify output location", file=out)
+        print(row, file=out)
+    return row
+
+
 def als_predict_console(lines, client, out=sys.stdout):
     """The query loop of flink-queryable-client/.../qs/ALSPredict.java:58-92 over a `formats.QueryableStateClient`: one
     `user,item` pair per line -> two state lookups ("<user>-U", "<item>-I"), the dot product of the parsed factor strings."""
@@ -213,11 +237,15 @@ def svm_predict_console(lines, client, outputDecisionFunction=False, thresholdVa
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
+    if argv and argv[0] == "als-mean":
+        als_mean_vector(argv[1:])
+        return 0
     if not argv or argv[0] not in ("als", "svm"):
         print("usage: python -m flinkms_b200 als --input ratings.csv [--fieldDelimiter comma|tab] [--ignoreFirstLine true] "
               "[--iterations 10] [--numFactors 10] [--lambda 0.9] [--seed 42] [--userFactors U.txt --itemFactors I.txt]\n"
               "       python -m flinkms_b200 svm --training data.libsvm [--blocks 10] [--iteration 10] [--partition true --range 1000] "
-              "[--output model.txt]", file=sys.stderr)
+              "[--output model.txt]\n"
+              "       python -m flinkms_b200 als-mean --type user|item --input U.txt [--output mean.txt]", file=sys.stderr)
         return 2
     (als_impl if argv[0] == "als" else svm_impl)(argv[1:])
     return 0

@@ -102,3 +102,22 @@ def test_predict_consoles_follow_the_reference_clients():
     out = io.StringIO()
     jobs.svm_predict_console(["1:2.0 4:0.5"], client, True, 0.0, out)
     assert "SVM Prediction =  %f " % (0.25 * 2.0 + 2.0 * 0.5) in out.getvalue()
+
+
+def test_als_mean_vector_job(tmp_path):
+    """ALSMeanVector.scala:12-48: left-to-right fp64 sum / count, formatted like Scala's mkString of doubles."""
+    rows = ["3,U,0.1;0.2;-1.5", "9,U,0.3;0.4;2.5", "11,U,1.0E-4;5.0;0.25"]
+    src = tmp_path / "U.txt"
+    src.write_text("\n".join(rows) + "\n")
+    out = io.StringIO()
+    row = jobs.als_mean_vector(["--type", "user", "--input", str(src)], out=out)
+    m = [((0.1 + 0.3) + 1.0e-4) / 3, ((0.2 + 0.4) + 5.0) / 3, ((-1.5 + 2.5) + 0.25) / 3]
+    assert row == "MEAN,U," + ";".join(formats.java_double_to_string(v) for v in m)
+    assert out.getvalue().splitlines() == ["Printing results to stdout. Use --output to specify output location", row]
+    dst = tmp_path / "mean.txt"
+    jobs.als_mean_vector(["--type", "item", "--input", str(src), "--output", str(dst)])
+    assert dst.read_text() == row.replace("MEAN,U,", "MEAN,I,") + "\n"
+    with pytest.raises(ValueError):
+        jobs.als_mean_vector(["--type", "both", "--input", str(src)])
+    with pytest.raises(RuntimeError):
+        jobs.als_mean_vector(["--input", str(src)])
