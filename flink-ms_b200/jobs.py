@@ -82,8 +82,15 @@ class ParameterTool:
     def getDouble(self, key, default=None):
         return float(self.data[key]) if key in self.data else default
 
-    def getBoolean(self, key, default=False):
-        return self.data[key].lower() == "true" if key in self.data else default     # Boolean.valueOf
+    _REQUIRED = object()
+
+    def getBoolean(self, key, default=_REQUIRED):
+        """getBoolean(key) without a default is getRequired + Boolean.valueOf, like Flink's."""
+        if key not in self.data:
+            if default is ParameterTool._REQUIRED:
+                raise RuntimeError(f"No data for required key '{key}'")
+            return default
+        return self.data[key].lower() == "true"                                     # Boolean.valueOf
 
 
 def _write_text(path, rows):
@@ -150,7 +157,8 @@ def svm_impl(argv, ctx: N.Context | None = None, out=sys.stdout):
             svm.setSeed(params.getLong("seed"))                                     # not a flag of the reference job (its seed is random)
         svm.fit(None, y, parallelism=params.getInt("parallelism", 1), csr=csr, dim=dim)
         weights = svm.weightsOption[0].data
-        rows = svm_model_rows(weights, partition=params.getBoolean("partition", False), range_=params.getInt("range", 1000))
+        # params.getBoolean("partition") has no default in the reference (SVMImpl.scala:41): the flag is required
+        rows = svm_model_rows(weights, partition=params.getBoolean("partition"), range_=params.getInt("range", 1000))
         if params.has("output"):
             _write_text(params.get("output"), rows)
         else:
@@ -243,7 +251,7 @@ def main(argv=None):
     if not argv or argv[0] not in ("als", "svm"):
         print("usage: python -m flinkms_b200 als --input ratings.csv [--fieldDelimiter comma|tab] [--ignoreFirstLine true] "
               "[--iterations 10] [--numFactors 10] [--lambda 0.9] [--seed 42] [--userFactors U.txt --itemFactors I.txt]\n"
-              "       python -m flinkms_b200 svm --training data.libsvm [--blocks 10] [--iteration 10] [--partition true --range 1000] "
+              "       python -m flinkms_b200 svm --training data.libsvm --partition true|false [--range 1000] [--blocks 10] [--iteration 10] "
               "[--output model.txt]\n"
               "       python -m flinkms_b200 als-mean --type user|item --input U.txt [--output mean.txt]", file=sys.stderr)
         return 2

@@ -17,6 +17,8 @@ def test_parameter_tool_from_args():
     assert p.get("input") == "a.csv" and p.getInt("iterations") == 7 and p.getDouble("lambda") == -0.5
     assert p.has("flag") and p.get("flag") == jobs.ParameterTool.NO_VALUE_KEY
     assert p.getBoolean("ignoreFirstLine", True) is False and p.getBoolean("missing", True) is True
+    with pytest.raises(RuntimeError):
+        p.getBoolean("missing")
     assert p.getInt("missing", 3) == 3
     with pytest.raises(RuntimeError):
         p.getRequired("training")
@@ -64,7 +66,7 @@ def test_svm_job_end_to_end(fms, ctx, tmp_path):
     src = tmp_path / "train.libsvm"
     src.write_text("".join(("%+d" % int(lab)) + "".join(f" {j + 1}:{float(v)!r}" for j, v in enumerate(row) if v != 0.0) + "\n" for lab, row in zip(y, X)))
     dst = tmp_path / "model.txt"
-    jobs.svm_impl(["--training", str(src), "--blocks", "3", "--iteration", "4", "--seed", "9", "--output", str(dst)], ctx=ctx)
+    jobs.svm_impl(["--training", str(src), "--blocks", "3", "--iteration", "4", "--seed", "9", "--partition", "false", "--output", str(dst)], ctx=ctx)
     w_job = formats.parse_svm_rows(dst.read_text().splitlines(), dim=X.shape[1])
     w_orc = oracle.svm_fit(X, y, np.zeros(len(y), np.int32), 3, 4, 10, 1.0, 1.0, 9)    # parallelism 1: every row in block 0
     assert np.abs(w_job - w_orc).max() <= 1e-4 * max(1.0, np.abs(w_orc).max())
@@ -75,6 +77,9 @@ def test_svm_job_end_to_end(fms, ctx, tmp_path):
     assert lines[0].startswith("Printing result to stdout.") and lines[1].startswith("0,1:") and lines[2].startswith("1,4:")
     with pytest.raises(RuntimeError):
         jobs.svm_impl(["--blocks", "3"], ctx=ctx)
+    with pytest.raises(RuntimeError) as ei:                                         # --partition is required (getBoolean without default)
+        jobs.svm_impl(["--training", str(src), "--seed", "9"], ctx=ctx)
+    assert "partition" in str(ei.value)
 
 
 def test_predict_consoles_follow_the_reference_clients():
