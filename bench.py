@@ -113,6 +113,16 @@ def svm_bytes_step(dim):
     return 4 * dim + 12
 
 
+def host_threads():
+    """Threads for the CPU legs: the cores this process may run on.  Not omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to every rank, which would turn the reference arm at N > 1 into a single-threaded run."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 256))
+
+
 def cpu_als_sample(args, d, threads):
     """Bounded CPU sample of the same workload: same rank, same row-length regime for users (~100 ratings/user)."""
     import oracle
@@ -130,7 +140,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import oracle
-    threads = oracle.num_threads()
+    threads = host_threads()
     d = args.rank
     orc, nnz, sample = cpu_als_sample(args, d, threads)
     for _ in range(args.warmup_ref):
@@ -354,7 +364,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         import oracle
-        threads = oracle.num_threads()
+        threads = host_threads()
         orc, cn, sample = cpu_als_sample(args, d, threads)
         t0 = time.perf_counter()
         orc.half_step(0, 0.9, threads)
