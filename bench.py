@@ -33,8 +33,11 @@ def log(*a):
 
 def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    return json.load(open(p)) if os.path.exists(p) else {}
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p))
+    return {}
 
 
 def full_config(args, world):
@@ -113,14 +116,42 @@ def svm_bytes_step(dim):
     return 4 * dim + 12
 
 
+def cgroup_cpu_quota():
+    """CPUs the container may use per its cgroup CPU bandwidth limit (None = unlimited / unknown)."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]                      # cgroup v2
+        return None if q == "max" else float(q) / float(per)
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())                   # cgroup v1
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def host_threads():
-    """Threads for the CPU legs: the cores this process may run on.  Not omp_get_max_threads(): torchrun exports
-    OMP_NUM_THREADS=1 to every rank, which would turn the reference arm at N > 1 into a single-threaded run."""
+    """Threads for the CPU legs: the cores this process may run on, capped by the cgroup CPU quota (more threads than
+    quota only buys throttling: round 1 saw a 6x swing of the CPU arm between two "128-core" boxes).  Not
+    omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every rank, which would turn the reference arm at
+    N > 1 into a single-threaded run."""
     try:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
         n = os.cpu_count() or 1
+    q = cgroup_cpu_quota()
+    if q is not None:
+        n = min(n, max(1, int(q)))
     return max(1, min(n, 256))
+
+
+def cpu_info(threads):
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except AttributeError:
+        aff = os.cpu_count()
+    return {"cores": threads, "affinity_cores": aff, "cgroup_cpu_quota": cgroup_cpu_quota()}
 
 
 def cpu_als_sample(args, d, threads):
@@ -135,8 +166,29 @@ def cpu_als_sample(args, d, threads):
     return orc, len(u), f"ALS rank {d}, {U} users x {I} items, {len(u)} ratings (same generator), 1 iteration"
 
 
+def cpu_svm_sample(args, threads, rounds=10):
+    """Bounded CPU sample of the SVM workload: same dim, same block size n_k as the GPU run (K scaled with n), one epoch
+    per round, `rounds` rounds of the oracle's CoCoA loop on all host threads (blocks are independent inside a round)."""
+    import oracle
+    synth = importlib.import_module("flink-ms_b200.synth")
+    nk = max(1, args.svm_n // args.svm_blocks)
+    Ks = max(1, args.cpu_svm_n // nk)
+    ns = Ks * nk
+    X, y, _ = synth.svm_data(ns, args.svm_dim, seed=1234)
+    bid = (np.arange(ns, dtype=np.int64) % Ks).astype(np.int32)
+    t0 = time.perf_counter()
+    oracle.svm_fit(X, y, bid, Ks, rounds, -1, 1.0, 1.0, 42, 0, threads)
+    dt = time.perf_counter() - t0
+    info = cpu_info(threads)
+    info.update({"value": ns * rounds / dt, "unit": "samples/s/epoch", "kind": "port", "seconds": dt,
+                 "sample": f"CoCoA/SDCA {ns} x {args.svm_dim} dense fp32 (same generator), K={Ks} blocks of n_k={nk} rows, "
+                           f"H = n_k, {rounds} rounds, fp64 oracle port, {threads} threads"})
+    return info
+
+
 def run_reference(args, rank, world):
-    """Reference arm: the FlinkML CPU algorithm (oracle port -- the Flink jar cannot run here) on host cores."""
+    """Reference arm: the FlinkML CPU algorithm (oracle port -- the Flink jar cannot run here) on host cores, on a
+    BOUNDED SAMPLE of the workload (stated in config.workload and cpu_baseline.sample)."""
     if rank != 0:
         return
     import oracle
@@ -151,23 +203,118 @@ def run_reference(args, rank, world):
         orc.half_step(1, 0.9, threads)
     dt = time.perf_counter() - t0
     v = nnz * args.steps / dt
+    cfg = workload_config(args, world, None)
+    cfg["workload"] += f" -- CPU arm timed on a bounded sample of it: {sample}"
+    cfg["parallelism"] = f"OpenMP over rows, {threads} host threads"
+    cb = cpu_info(threads)
+    cb.update({"value": v, "unit": "ratings/s/iter", "kind": "port", "sample": sample})
+    svm = None
+    if not args.skip_svm:
+        sv = cpu_svm_sample(args, threads)
+        svm = {"impl": "reference", "metric": "svm_samples_per_sec_per_epoch", "value": sv["value"], "unit": "samples/s/epoch",
+               "cpu_baseline": sv, "e2e": {"value": sv["value"], "unit": "samples/s/epoch", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     line = {"impl": "reference", "metric": "als_ratings_per_sec_per_iter", "value": v, "unit": "ratings/s/iter",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup_ref, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world),
-            "cpu_baseline": {"value": v, "unit": "ratings/s/iter", "cores": threads, "kind": "port", "sample": sample},
+            "config": cfg, "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "ratings/s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "svm": svm}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
+def workload_config(args, world, p2p):
+    """p2p: what the run really did (None: not applicable), not what the flags asked for."""
+    cfgno = {64: "configs[1]", 128: "configs[2]"}.get(args.rank, "configs[1] shape")
+    if world == 1:
+        par = "1 GPU"
+    elif p2p:
+        par = (f"rows sharded over {world} GPUs, one process per GPU; solver warps store each new gather-plane row into every "
+               f"replica over NVLink (CUDA IPC peer mappings), one cross-rank barrier per half-step")
+    else:
+        par = f"rows sharded over {world} GPUs, one process per GPU; NCCL all-gather of the solved shard after every half-step"
     return {"workload": f"ALS rank={args.rank}, {args.users} users x {args.items} items, {args.nnz} synthetic ratings "
-                        f"(BASELINE.json configs[1]); lambda=0.9 seed=42; step = 1 ALS iteration (2 half-steps)",
-            "parallelism": (f"rows sharded over {world} GPU(s); "
-                            + ("solver warps store each new gather-plane row into every replica over NVLink (CUDA IPC), barrier per half-step"
-                               if getattr(args, "als_p2p", 1) else "NCCL all-gather of the gather-plane shards")) if world > 1 else "1 GPU",
+                        f"(BASELINE.json {cfgno}); lambda=0.9 seed=42; step = 1 ALS iteration (2 half-steps)",
+            "parallelism": par,
             "l2": "inputs larger than L2 (CSR pair 1.6 GB + factors 0.28 GB per iteration vs 126 MB L2); no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------ bench-scale parity
+def _partner_rows_f64(backend, partner, d, idx_t):
+    """The exact partner values the half-step kernel consumed for dense partner indices idx_t (device int64 tensor):
+    hi + lo / 2048 of the fp16 gather planes on the tensor-core path, the fp32 rows otherwise.  float64, on the host."""
+    planes = backend.plane_tensors(partner, d)
+    if planes is not None:
+        pl = planes[0].index_select(0, idx_t)
+        return (pl[:, :d].double() + pl[:, d:].double() / 2048.0).cpu().numpy()
+    return backend.factor_tensor(partner, d).index_select(0, idx_t).double().cpu().numpy()
+
+
+def als_parity_side(ctx, backend, which, lam, d, h_t, h_p, h_r, n_side, n_partner, rank, world, dev, samples, shard_range):
+    """Rows of side `which` (0 users / 1 items) were just solved from the partner side's current values.  Take `samples`
+    random rows of this rank's shard, rebuild each row's normal equations in fp64 from the exact partner values the
+    kernel read and the host COO, solve them with LAPACK and compare with the device's row (max-norm relative error)."""
+    import torch
+    rb, re_, _ = shard_range(n_side, world, rank)
+    if re_ <= rb:
+        return 0.0, 0
+    rng = np.random.default_rng(4242 + 17 * which + rank)
+    rows = np.sort(rng.choice(re_ - rb, size=min(samples, re_ - rb), replace=False)) + rb
+    lut = np.full(n_side, -1, np.int32)
+    lut[rows] = np.arange(len(rows), dtype=np.int32)
+    slot = lut[h_t]                                                 # bench ids are dense (checked by the caller)
+    sel = np.flatnonzero(slot >= 0)
+    order = np.argsort(slot[sel], kind="stable")
+    sel = sel[order]
+    starts = np.searchsorted(slot[sel], np.arange(len(rows) + 1))
+    P = _partner_rows_f64(backend, 1 - which, d, torch.from_numpy(h_p[sel]).to(dev))
+    R = h_r[sel]
+    worst = 0.0
+    for k, row in enumerate(rows):
+        a, b = starts[k], starts[k + 1]
+        Y = P[a:b]
+        A = Y.T @ Y + lam * (b - a) * np.eye(d)
+        x_ref = np.linalg.solve(A, Y.T @ R[a:b])
+        _, x_dev = ctx.als_get_factor_rows(which, int(row), int(row) + 1)
+        worst = max(worst, float(np.abs(x_dev[0] - x_ref).max() / np.abs(x_ref).max()))
+    return worst, len(rows)
+
+
+def svm_parity(ctx, dsvm, oracle, X, y_host, n, dim, K, rank, world, rounds_done, blocks_to_check=8, seed=42, lam=1.0):
+    """Replays `blocks_to_check` whole blocks of ONE more CoCoA round in fp64 (numpy restatement of localDualMethod /
+    maximize, the java.util.Random index stream from the oracle) from the device's w / alpha snapshot and compares the
+    device's alpha after the round and the block's delta-w."""
+    w0 = ctx.svm_get_weights(dim)
+    a0 = ctx.svm_get_alpha()
+    dsvm.round(-1)
+    a1 = ctx.svm_get_alpha()
+    ln = lam * n
+    worst_a, worst_dw, checked = 0.0, 0.0, 0
+    for k in range(rank, K, world):
+        if checked >= blocks_to_check:
+            break
+        rows = np.arange(k, n, K)
+        nk = len(rows)
+        if nk == 0:
+            continue
+        stream = oracle.svm_index_stream(seed, k, nk, (rounds_done + 1) * nk)[-nk:]
+        import torch
+        Xk = X[torch.from_numpy(rows).to(X.device)].double().cpu().numpy()
+        yk = y_host[rows]
+        wl, tmp, dw = w0.copy(), a0[rows].copy(), np.zeros(dim)
+        for idx in stream:
+            x, yy = Xk[idx], yk[idx]
+            g = (yy * float(x @ wl) - 1.0) * ln
+            if g != 0.0:
+                q = float(x @ x)
+                an = min(max(tmp[idx] - g / q, 0.0), 1.0) if q != 0.0 else 1.0
+                step = x * (yy * (an - tmp[idx]) / ln)
+                wl += step; dw += step
+                tmp[idx] = an
+        worst_a = max(worst_a, float(np.abs(a1[rows] - tmp).max()))
+        dw_dev = ((a1[rows] - a0[rows]) * yk / ln) @ Xk
+        worst_dw = max(worst_dw, float(np.abs(dw_dev - dw).max() / max(np.abs(dw).max(), 1e-300)))
+        checked += 1
+    return {"blocks_checked": checked, "alpha_max_abs_diff": worst_a, "delta_w_max_rel": worst_dw}
 
 
 def main():
@@ -182,8 +329,12 @@ def main():
     ap.add_argument("--rank", type=int, default=64)
     ap.add_argument("--svm-n", type=int, default=10_000_000)
     ap.add_argument("--svm-dim", type=int, default=1024)
-    ap.add_argument("--svm-blocks-per-gpu", type=int, default=3552)
-    ap.add_argument("--svm-rounds", type=int, default=3)
+    ap.add_argument("--svm-blocks", type=int, default=28416,
+                    help="CoCoA blocks K, the SAME for every N (the model depends on K): 3552 warps per GPU at 8 GPUs")
+    ap.add_argument("--svm-rounds", type=int, default=10)
+    ap.add_argument("--cpu-svm-n", type=int, default=500_000)
+    ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--parity-rows", type=int, default=512)
     ap.add_argument("--skip-svm", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -294,6 +445,40 @@ def main():
                 "iteration": {"achieved": iter_gbs, "frac": iter_gbs / peak, "ms_users": ms_user, "ms_items": ms_item}}
     clocks = clk.summary()
 
+    # ---------------------------------------------------------------------------------------- parity at bench scale
+    # Not timed.  The device state here is the one the timed loop left: items were just solved from the current users.
+    parity = None
+    if not args.skip_parity:
+        import zlib
+        t0 = time.perf_counter()
+        hu, hi, hr = h_u.numpy(), h_i.numpy(), h_r.numpy()
+        dense_ids = (n_users == int(hu.max()) + 1) and (n_items == int(hi.max()) + 1)      # synthetic ids are 0 .. N-1
+        parity = {"tolerance": 1e-5, "reference": "fp64 LAPACK solve of each sampled row's normal equations from the exact partner "
+                                                  "values the kernel read (hi + lo/2048 of the gather planes) and the host COO"}
+        if dense_ids:
+            e_items, n_i = als_parity_side(ctx, backend, 1, 0.9, d, hi, hu, hr, n_items, n_users, rank, world, dev, args.parity_rows, D.shard_range)
+            dals.half_step(0, 0.9)                                                       # users from the current items
+            ctx.synchronize()
+            barrier()
+            e_users, n_u = als_parity_side(ctx, backend, 0, 0.9, d, hu, hi, hr, n_users, n_items, rank, world, dev, args.parity_rows, D.shard_range)
+            parity.update({"als_items_max_rel": max_over_ranks(e_items), "als_users_max_rel": max_over_ranks(e_users),
+                           "rows_checked_per_rank": [n_u, n_i]})
+            parity["max_rel"] = max(parity["als_items_max_rel"], parity["als_users_max_rel"])
+        else:
+            parity["skipped"] = "ids are not dense 0..N-1"
+        # CRC of both fp32 factor matrices after (warmup + steps) iterations + 1 users half-step: per-row arithmetic does
+        # not depend on the sharding, so the value must be IDENTICAL at every N
+        dals.finalize()
+        ctx.synchronize()
+        barrier()
+        if rank == 0:
+            fu = backend.factor_tensor(0, d)[:n_users].cpu().numpy()
+            fi = backend.factor_tensor(1, d)[:n_items].cpu().numpy()
+            parity["factors_crc"] = f"{zlib.crc32(fu.tobytes()):08x}-{zlib.crc32(fi.tobytes()):08x}"
+            parity["factors_crc_of"] = f"fp32 U ({n_users}x{d}) and I ({n_items}x{d}) after {args.warmup + args.steps} iterations + 1 users half-step"
+            parity["bad_rows_last_half_step"] = ctx.als_last_info()
+        parity["seconds"] = time.perf_counter() - t0
+
     # ---------------------------------------------------------------------------------------- e2e through the C-ABI
     e2e = None
     if not args.skip_e2e:
@@ -370,8 +555,8 @@ def main():
         orc.half_step(0, 0.9, threads)
         orc.half_step(1, 0.9, threads)
         dt = time.perf_counter() - t0
-        cpu = {"value": cn / dt, "unit": "ratings/s/iter", "cores": threads, "kind": "port", "sample": sample,
-               "seconds": dt}
+        cpu = cpu_info(threads)
+        cpu.update({"value": cn / dt, "unit": "ratings/s/iter", "kind": "port", "sample": sample, "seconds": dt})
 
     # ---------------------------------------------------------------------------------------- SVM (configs[3])
     svm = None
@@ -385,8 +570,8 @@ def main():
         line = {"metric": "als_ratings_per_sec_per_iter", "value": value, "unit": "ratings/s/iter", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": gpu_launches_als, "clocks": clocks, "svm": svm, "predict": predict}
+                "config": workload_config(args, world, p2p), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": gpu_launches_als, "clocks": clocks, "parity": parity, "svm": svm, "predict": predict}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -395,19 +580,20 @@ def main():
 def bench_svm(args, fms, D, synth, dev, rank, world, local_rank, peak, peak_src, barrier, max_over_ranks):
     import torch
     n, dim = args.svm_n, args.svm_dim
-    K = args.svm_blocks_per_gpu * world
+    K = args.svm_blocks                                   # fixed for every N: the trained model depends on K
     t0 = time.perf_counter()
     X, y, _ = synth.svm_data_torch(n, dim, dev, seed=1234)
     torch.cuda.synchronize()
     log(f"[rank {rank}] SVM data {n}x{dim} generated in {time.perf_counter() - t0:.1f}s")
     bid = (np.arange(n, dtype=np.int64) % K).astype(np.int32)
+    y_host = y.double().cpu().numpy()
     ctx = fms.Context(local_rank)
     ctx.svm_set_kernel(args.svm_kernel)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    ctx.svm_load(None, y.double().cpu().numpy(), bid, K, rank, world, 1.0, 1.0, 42, dim=dim, device_ptr=X.data_ptr())
+    ctx.svm_load(None, y_host, bid, K, rank, world, 1.0, 1.0, 42, dim=dim, device_ptr=X.data_ptr())
     dsvm = D.DistributedSVM(D.ContextSVMBackend(ctx, dev))
-    rounds = args.svm_rounds
-    for _ in range(3):
+    rounds, warm = args.svm_rounds, 3
+    for _ in range(warm):
         dsvm.round(-1)
     barrier()
     l0 = ctx.launch_count
@@ -418,6 +604,7 @@ def bench_svm(args, fms, D, synth, dev, rank, world, local_rank, peak, peak_src,
             dsvm.round(-1)
         e1.record(stream)
         barrier()
+    launches = ctx.launch_count - l0
     ms = max_over_ranks(e0.elapsed_time(e1)) / rounds
     w = ctx.svm_get_weights(dim)
     assert np.isfinite(w).all()
@@ -425,17 +612,64 @@ def bench_svm(args, fms, D, synth, dev, rank, world, local_rank, peak, peak_src,
     steps_per_rank = n / world
     achieved = svm_bytes_step(dim) * steps_per_rank / (ms * 1e-3) / 1e9
     out = {"metric": "svm_samples_per_sec_per_epoch", "value": n / (ms * 1e-3), "unit": "samples/s/epoch",
-           "ms_per_round": ms, "rounds": rounds, "warmup": 3, "dtype": "f32",
+           "ms_per_round": ms, "rounds": rounds, "warmup": warm, "dtype": "f32", "n_gpus": world,
            "config": {"workload": f"CoCoA/SDCA linear SVM, {n} x {dim} dense fp32 synthetic (BASELINE.json configs[3]); "
-                                  f"K={K} blocks (block_id = i mod K), H = n_k (one epoch per round), lambda=1 "
-                                  f"stepsize=1 seed=42", "l2": "X is 41 GB, far larger than L2"},
+                                  f"K={K} blocks for every N (block_id = i mod K, n_k = {n // K}), H = n_k (one epoch per round), "
+                                  f"lambda=1 stepsize=1 seed=42",
+                      "parallelism": "1 GPU" if world == 1 else f"blocks k = g mod {world} on GPU g; delta-w all-reduced per round",
+                      "l2": "X is 41 GB, far larger than L2"},
            "roofline": {"bound": "hbm", "kernel": "SVM block sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak,
                         "traffic": load_traffic().get("svm_block_sweep") if (world == 1 and n == 10_000_000 and dim == 1024) else None,
                         "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": svm_bytes_step(dim) * steps_per_rank, "ms_per_launch": ms},
-           "gpu_launches": ctx.launch_count - l0, "train_accuracy_first_100k": acc, "clocks": clk.summary()}
+           "gpu_launches": launches, "train_accuracy_first_100k": acc, "clocks": clk.summary(),
+           "w_checksum": {"l2": float(np.sqrt((w * w).sum())), "sum": float(w.sum()), "first4": [float(v) for v in w[:4]],
+                          "after_rounds": warm + rounds}}
+    # ---- parity at bench scale: replay whole blocks of one more round in fp64 from the device's snapshot
+    if not args.skip_parity:
+        import oracle
+        t0 = time.perf_counter()
+        pr = svm_parity(ctx, dsvm, oracle, X, y_host, n, dim, K, rank, world, warm + rounds)
+        pr["alpha_max_abs_diff"] = max_over_ranks(pr["alpha_max_abs_diff"])
+        pr["delta_w_max_rel"] = max_over_ranks(pr["delta_w_max_rel"])
+        pr["blocks_checked"] = f"{pr['blocks_checked']} per rank"
+        pr["tolerance"] = "alpha 1e-4 abs, delta-w 1e-4 rel (fp32 device vs fp64 replay of the same steps)"
+        pr["seconds"] = time.perf_counter() - t0
+        out["parity"] = pr
     ctx.close()
+    # ---- e2e through the C-ABI: host fp32 X (pinned) -> fms_svm_fit -> w on the host.  N = 1 only: the sharded run keeps
+    #      X on the device and has no host-buffer entry point that avoids uploading the full matrix to every rank.
+    out["e2e"] = None
+    if world == 1 and not args.skip_e2e:
+        try:
+            t0 = time.perf_counter()
+            hX = torch.empty((n, dim), dtype=torch.float32, pin_memory=True)
+            hX.copy_(X)
+            torch.cuda.synchronize()
+            t_pin = time.perf_counter() - t0
+            T = min(rounds, 10)
+            ctx2 = fms.Context(local_rank)
+            ctx2.svm_set_kernel(args.svm_kernel)
+            t0 = time.perf_counter()
+            w2 = ctx2.svm_fit(hX.numpy(), y_host, bid, K, T, -1, 1.0, 1.0, 42)
+            t_fit = time.perf_counter() - t0
+            assert np.isfinite(w2).all()
+            out["e2e"] = {"value": n * T / t_fit, "unit": "samples/s/epoch", "seconds": t_fit, "rounds": T,
+                          "h2d_bytes_per_step": int((n * dim * 4 + n * 8 + n * 4) // T), "d2h_bytes_per_step": int(dim * 8 // T),
+                          "gpu_launches": ctx2.launch_count,
+                          "note": f"one fms_svm_fit call: pinned host X ({n * dim * 4 / 1e9:.1f} GB fp32) + labels + block ids H2D, {T} CoCoA rounds, "
+                                  f"w D2H; bytes are per call / rounds (pinning + filling the host buffer took {t_pin:.1f} s, not timed)"}
+            ctx2.close()
+            del hX
+        except Exception as e:  # noqa: BLE001  (host memory for 41 GB of pinned X not available)
+            out["e2e"] = {"value": None, "error": repr(e)}
+    # ---- CPU baseline (rank 0, N = 1): the oracle port on a bounded sample, all host threads
+    out["cpu_baseline"] = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        del X
+        torch.cuda.empty_cache()
+        out["cpu_baseline"] = cpu_svm_sample(args, host_threads())
     return out
 
 

@@ -309,6 +309,8 @@ int als_sgd_step_device(fms_ctx *ctx, const int64_t *d_u, const int64_t *d_i, co
     AlsState &A = ctx->als;
     if (n <= 0) return FMS_OK;
     if (n >= ((int64_t)1 << 31)) return fail(ctx, FMS_ERR_UNSUPPORTED, "sgd batch too large");
+    // k_als_sgd keeps four components per lane (rank <= 128); fms_als_set_model accepts any rank, so refuse here
+    if (A.rank > 128) return fail(ctx, FMS_ERR_UNSUPPORTED, "fms_als_sgd_step: rank %d > 128 is not supported", A.rank);
     DevBuf<int64_t> row_u, row_i;
     DevBuf<int> win_u, win_i;
     FMS_CUDA(ctx, row_u.alloc((size_t)n));

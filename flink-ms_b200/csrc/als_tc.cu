@@ -34,6 +34,7 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "chol_mma.cuh"
 
 namespace fms {
 namespace tc {
@@ -709,6 +710,297 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
     }
 }
 
+// =====================================================================================================================
+// Kernel v2 (round 2).  Same producers and MMA issuer; what changed is everything behind the accumulator:
+//   * the epilogue warps read TMEM with tcgen05.ld.16x256b -- the register layout of an mma.sync accumulator -- and hand the
+//     NEGATED system over as 16x8 fragment tiles (chol_mma.cuh "tile layout"): 4 FFMA + 1 STS.128 per tile instead of a
+//     predicated scalar store per matrix entry (1 430 -> ~300 warp instructions per system);
+//   * the solver warps factor it on the warp-level tensor path (cm::solve_tiles: blocked right-looking Cholesky, 3xTF32
+//     HMMA for the triangular solves and trailing updates, forward substitution as one more matrix row);
+//   * ring depth and the number of ACTIVE solver warps are template parameters: the long-row half-step (few systems, every
+//     stage a DRAM gather) trades solver buffers for a deeper ring -- gathers in flight are what paces it (Little's law:
+//     13 stages x 6 KB against ~2.5 us of loaded DRAM latency is one stage per ~200 cycles).
+// 24 warps: epilogue 0-3 | solvers 4-15 | MMA 16 | producers 17-23.
+constexpr int V2_WARPS = 24, V2_W_SOLVE0 = 4, V2_N_SOLVE = 12, V2_W_MMA = 16, V2_W_PROD0 = 17;
+constexpr int V2_REGS_EPI = 72, V2_REGS_SOLVE = 104, V2_REGS_AUX = 40;     // (4 x 72 + 12 x 104 + 8 x 40) x 32 <= 768 x 80
+using TL4 = cm::Tiles<4>;
+constexpr int V2_BUF_FLOATS = TL4::FLOATS + 3 * D;                          // tiles | bz | invd | xs  per solver warp
+
+template <int NSTG_, int NSA>
+struct Smem2 {
+    static constexpr int ring = 0;
+    static constexpr int bufs = ring + NSTG_ * STAGE_BYTES;
+    static constexpr int bars = bufs + NSA * V2_BUF_FLOATS * 4;
+    static constexpr int n_bars = 2 * NSTG_ + 2 * NACC + 2 * NSA;
+    static constexpr int tmem_ptr = bars + n_bars * 8;
+    static constexpr int total = tmem_ptr + 16;
+};
+
+__device__ __forceinline__ void tc_ld16x256_x4(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld16x256_x1(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <bool DUMP, bool LDGSTS, int NSTG_, int NSA>
+__global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64_v2(
+    const __grid_constant__ CUtensorMap map_pl, const int64_t *__restrict__ ptr,
+    const int32_t *__restrict__ stage_ptr, const int32_t *__restrict__ colp, const float *__restrict__ valp,
+    const int32_t *__restrict__ cta_rows, float *__restrict__ T, __half *__restrict__ T_pl, float lambda,
+    int64_t row_begin, int *__restrict__ info, float *__restrict__ dump, __half *const *__restrict__ peers, int n_peers,
+    const __half *__restrict__ S_pl) {
+    using SM = Smem2<NSTG_, NSA>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
+    const uint32_t sm_base = smem_u32(sm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = sm_base + SM::bars;
+    auto bar_full = [&](int s) { return bar0 + 8u * s; };
+    auto bar_empty = [&](int s) { return bar0 + 8u * (NSTG_ + s); };
+    auto bar_acc_full = [&](int a) { return bar0 + 8u * (2 * NSTG_ + a); };
+    auto bar_acc_empty = [&](int a) { return bar0 + 8u * (2 * NSTG_ + NACC + a); };
+    auto bar_g_full = [&](int g) { return bar0 + 8u * (2 * NSTG_ + 2 * NACC + g); };
+    auto bar_g_empty = [&](int g) { return bar0 + 8u * (2 * NSTG_ + 2 * NACC + NSA + g); };
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sm + SM::tmem_ptr);
+
+    // zero the ring once: the R / R' chunks only ever get their first four bytes per row rewritten
+    for (int i = threadIdx.x; i < NSTG_ * STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(sm + SM::ring)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTG_; ++s) { mbar_init(bar_full(s), LDGSTS ? 33 : 1); mbar_init(bar_empty(s), 1); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(bar_acc_full(a), 1); mbar_init(bar_acc_empty(a), N_EPI); }
+        for (int g = 0; g < NSA; ++g) { mbar_init(bar_g_full(g), N_EPI); mbar_init(bar_g_empty(g), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == V2_W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sm_base + SM::tmem_ptr) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();                                           // the zero fill must be visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t first = cta_rows[blockIdx.x], last = cta_rows[blockIdx.x + 1];
+
+    if (warp >= V2_W_MMA) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V2_REGS_AUX));
+      if (warp >= V2_W_PROD0) {
+        // ================================================================== producers (unchanged from v1)
+        const uint32_t pw = (uint32_t)(warp - V2_W_PROD0);
+        const int64_t s_lo = stage_ptr[first], s_hi = stage_ptr[last];
+        const uint32_t n_local = (uint32_t)(s_hi - s_lo);
+        const int32_t *cp = colp + s_lo * KROWS + (lane & 15);
+        const float *vp = valp + s_lo * KROWS + (lane & 15);
+        int idx0 = 0, idx1 = 0;
+        float rt0 = 0.f, rt1 = 0.f;
+        if (pw < n_local) { idx0 = cp[(int64_t)pw * KROWS]; rt0 = vp[(int64_t)pw * KROWS]; }
+        if (pw + N_PROD < n_local) { idx1 = cp[(int64_t)(pw + N_PROD) * KROWS]; rt1 = vp[(int64_t)(pw + N_PROD) * KROWS]; }
+        for (uint32_t c = pw; c < n_local; c += N_PROD) {
+            int idx2 = 0;
+            float rt2 = 0.f;
+            if (c + 2 * N_PROD < n_local) { idx2 = cp[(int64_t)(c + 2 * N_PROD) * KROWS]; rt2 = vp[(int64_t)(c + 2 * N_PROD) * KROWS]; }
+            const int slot = c % NSTG_;
+            const uint32_t stage = sm_base + SM::ring + slot * STAGE_BYTES;
+            if (LDGSTS) {
+                const int rq = lane >> 3, jc = lane & 7;
+                int ri[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ri[k] = __shfl_sync(0xffffffffu, idx0, 4 * k + rq);
+                mbar_wait(bar_empty(slot), ((c / NSTG_) & 1) ^ 1);
+                if (lane < 16) {
+                    __half rh, rl;
+                    split_half(rt0, rh, rl);
+                    const uint32_t off = (uint32_t)lane * 128u + (((uint32_t)lane & 7u) << 4);
+                    const uint32_t w0 = (uint32_t)__half_as_ushort(rh) | ((uint32_t)__half_as_ushort(rl) << 16);
+                    const uint32_t w1 = (uint32_t)__half_as_ushort(rh) << 16;
+                    *reinterpret_cast<uint32_t *>(sm + SM::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + off) = w0;
+                    *reinterpret_cast<uint32_t *>(sm + SM::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + (off ^ 16u)) = w1;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int r = 4 * k + rq;
+                    const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((jc ^ (r & 7)) << 4);
+                    const char *src = reinterpret_cast<const char *>(S_pl) + (size_t)ri[k] * (PLANE_PITCH * 2) + (size_t)jc * 16;
+                    cp_async16(dst, src);
+                    cp_async16(dst + TILE_BYTES, src + D * 2);
+                }
+                cp_async_arrive_noinc(bar_full(slot));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full(slot));
+            } else {
+                int r[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = __shfl_sync(0xffffffffu, idx0, i);
+                mbar_wait(bar_empty(slot), ((c / NSTG_) & 1) ^ 1);
+                if (lane < 16) {
+                    __half rh, rl;
+                    split_half(rt0, rh, rl);
+                    const uint32_t off = (uint32_t)lane * 128u + (((uint32_t)lane & 7u) << 4);
+                    const uint32_t w0 = (uint32_t)__half_as_ushort(rh) | ((uint32_t)__half_as_ushort(rl) << 16);
+                    const uint32_t w1 = (uint32_t)__half_as_ushort(rh) << 16;
+                    *reinterpret_cast<uint32_t *>(sm + SM::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + off) = w0;
+                    *reinterpret_cast<uint32_t *>(sm + SM::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + (off ^ 16u)) = w1;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_expect_tx(bar_full(slot), 2 * TILE_BYTES);
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    tma_gather4_pair(stage + t * 512, stage + TILE_BYTES + t * 512, &map_pl, bar_full(slot), r[4 * t], r[4 * t + 1],
+                                     r[4 * t + 2], r[4 * t + 3]);
+            }
+            idx0 = idx1; rt0 = rt1;
+            idx1 = idx2; rt1 = rt2;
+        }
+      } else {
+        // ================================================================== MMA issuer (unchanged from v1)
+        uint32_t job = 0;
+        const uint32_t idesc1 = make_idesc(MMA_N1), idesc2 = make_idesc(MMA_N2);
+        constexpr uint32_t LBO_T = (uint32_t)(TILE_BYTES >> 4) << 16, LBO_B2 = (uint32_t)((2 * TILE_BYTES + 16) >> 4) << 16;
+        const uint32_t enc0 = ((sm_base + SM::ring) >> 4) & 0x3FFF;
+        uint32_t slot = 0, ph = 0, enc = enc0, ready = 0;
+        int nst = (first < last) ? stage_ptr[first + 1] - stage_ptr[first] : 0;
+        for (int64_t row = first; row < last; ++row, ++job) {
+            const int nst_next = (row + 1 < last) ? stage_ptr[row + 2] - stage_ptr[row + 1] : 0;
+            const int acc = job % NACC;
+            mbar_wait(bar_acc_empty(acc), ((job / NACC) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)acc * ACC_COLS;
+            for (int st = 0; st < nst; ++st) {
+                if (!ready) mbar_wait(bar0 + 8u * slot, ph);
+                tc_fence_after();
+                if (LDGSTS) fence_proxy_async();
+                uint32_t nslot = slot + 1, nph = ph, nenc = enc + (STAGE_BYTES >> 4);
+                if (nslot == NSTG_) { nslot = 0; nph ^= 1u; nenc = enc0; }
+                const uint32_t nready = mbar_test(bar0 + 8u * nslot, nph);
+                tc_stage_mma(d, enc | LBO_T, (enc + (TILE_BYTES >> 4)) | LBO_T, enc | LBO_B2, idesc1, idesc2, st > 0 ? 1u : 0u,
+                             bar0 + 8u * (NSTG_ + slot), bar_acc_full(acc), st == nst - 1 ? 1u : 0u);
+                slot = nslot; ph = nph; enc = nenc; ready = nready;
+            }
+            nst = nst_next;
+        }
+      }
+    } else if (warp < V2_W_SOLVE0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V2_REGS_EPI));
+        // ================================================================== epilogue: TMEM -> fragment tiles of -(G + lambda n I), -b
+        // M = 64 accumulator: rows 16 q .. 16 q + 15 live in the first 16 lanes of quadrant q == m-tile q of the system.
+        const int q = warp;
+        const int g8 = lane >> 2, t4 = lane & 3;
+        const bool dg0 = g8 == 2 * t4, dg1 = g8 == 2 * t4 + 1;      // this lane's entries on the diagonal of a diagonal tile
+        uint32_t job = 0;
+        for (int64_t row = first; row < last; ++row, ++job) {
+            const int acc = job % NACC, g = job % NSA;
+            const float reg = lambda * (float)(ptr[row + 1] - ptr[row]);
+            mbar_wait(bar_acc_full(acc), (job / NACC) & 1);
+            tc_fence_after();
+            mbar_wait(bar_g_empty(g), ((job / NSA) & 1) ^ 1);
+            float *buf = reinterpret_cast<float *>(sm + SM::bufs) + (size_t)g * V2_BUF_FLOATS;
+            float4 *tiles = reinterpret_cast<float4 *>(buf) + (q * (q + 1)) * 32 + lane;       // tile (q, j) at + 32 j
+            const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * ACC_COLS;
+#pragma unroll
+            for (int c0 = 0; c0 < 8; c0 += 4) {
+                if (c0 > 2 * q + 1) break;
+                float d1[16], d2[16];
+                tc_ld16x256_x4(tq + 8 * c0, d1);
+                tc_ld16x256_x4(tq + 64 + 8 * c0, d2);
+                tc_wait_ld();
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = c0 + jj;
+                    if (j <= 2 * q + 1) {
+                        float4 v;
+                        v.x = fmaf(-LO_INV, d2[4 * jj + 0], -d1[4 * jj + 0]);
+                        v.y = fmaf(-LO_INV, d2[4 * jj + 1], -d1[4 * jj + 1]);
+                        v.z = fmaf(-LO_INV, d2[4 * jj + 2], -d1[4 * jj + 2]);
+                        v.w = fmaf(-LO_INV, d2[4 * jj + 3], -d1[4 * jj + 3]);
+                        if (j == 2 * q) { v.x -= dg0 ? reg : 0.f; v.y -= dg1 ? reg : 0.f; }          // rows g   x cols 16 q + 2 t (+1)
+                        if (j == 2 * q + 1) { v.z -= dg0 ? reg : 0.f; v.w -= dg1 ? reg : 0.f; }      // rows g+8 x cols 16 q + 8 + 2 t (+1)
+                        tiles[32 * j] = v;
+                    }
+                }
+            }
+            float bb[4];
+            tc_ld16x256_x1(tq + 128, bb);                          // column 128: sum r_hi y, column 129: the 2^-11 terms
+            tc_wait_ld();
+            if (t4 == 0) {
+                float *bz = buf + TL4::FLOATS;
+                bz[16 * q + g8] = -fmaf(bb[1], LO_INV, bb[0]);
+                bz[16 * q + g8 + 8] = -fmaf(bb[3], LO_INV, bb[2]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar_acc_empty(acc)); mbar_arrive(bar_g_full(g)); }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(V2_REGS_SOLVE));
+        // ================================================================== solvers: one system per warp on the HMMA path
+        const int sv = warp - V2_W_SOLVE0;
+        if (sv < NSA) {
+            float *S = reinterpret_cast<float *>(sm + SM::bufs) + (size_t)sv * V2_BUF_FLOATS;
+            float *bz = S + TL4::FLOATS, *invd = bz + D, *xs = invd + D;
+            uint32_t use = 0;
+            for (int64_t row = first + sv; row < last; row += NSA) {
+                mbar_wait(bar_g_full(sv), use & 1);
+                ++use;
+                if (DUMP) {
+                    float *o = dump + (int64_t)(row - row_begin) * (D * D + D);
+                    for (int c = 0; c < D; ++c) {
+                        const int i0 = lane, i1 = lane + 32;
+                        o[i0 * D + c] = -S[c <= i0 ? TL4::at(i0, c) : TL4::at(c, i0)];
+                        o[i1 * D + c] = -S[c <= i1 ? TL4::at(i1, c) : TL4::at(c, i1)];
+                    }
+                    o[D * D + lane] = -bz[lane]; o[D * D + lane + 32] = -bz[lane + 32];
+                    __syncwarp();
+                }
+                float x[2];
+                cm::solve_tiles<4>(S, bz, invd, xs, lane, x);
+                const float b0 = x[0], b1 = x[1];
+                __half h0, l0, h1, l1;
+                split_half(b0, h0, l0);
+                split_half(b1, h1, l1);
+                __syncwarp();
+                // the plane row (256 B) is staged through this warp's scratch so that each lane stores 8 contiguous bytes
+                __half *stg = reinterpret_cast<__half *>(invd);
+                stg[lane] = h0; stg[lane + 32] = h1;
+                stg[D + lane] = l0; stg[D + 32 + lane] = l1;
+                __syncwarp();
+                const uint2 prow = reinterpret_cast<const uint2 *>(stg)[lane];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_g_empty(sv));          // tiles / scratch no longer needed
+                T[row * D + lane] = b0;
+                T[row * D + lane + 32] = b1;
+                const int64_t poff = row * PLANE_PITCH + 4 * lane;
+                if (n_peers == 0) {
+                    *reinterpret_cast<uint2 *>(T_pl + poff) = prow;
+                } else {
+                    for (int p = 0; p < n_peers; ++p) *reinterpret_cast<uint2 *>(peers[p] + poff) = prow;
+                }
+                const bool bad = !(fabsf(b0) <= 3.0e38f) || !(fabsf(b1) <= 3.0e38f);             // NaN / inf: the factorisation broke down
+                if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(info, 1);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == V2_W_MMA) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // fp32 factor rows -> gather planes (after init, after an all-gather, after the generic kernel wrote a side)
 __global__ void k_split_planes(const float *__restrict__ f, int64_t n, __half *__restrict__ pl) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -778,7 +1070,8 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 int als_tc_supported(const fms_ctx *ctx, int rank) {
-    return rank == tc::D && ctx->smem_optin >= (size_t)tc::Smem::total + 1024 && get_encode_fn() != nullptr;
+    constexpr size_t need = (size_t)(tc::Smem2<26, 6>::total > tc::Smem::total ? tc::Smem2<26, 6>::total : tc::Smem::total) + 1024;
+    return rank == tc::D && ctx->smem_optin >= need && get_encode_fn() != nullptr;
 }
 
 // planes of side s: [hi: rows x 64 halves][lo: rows x 64 halves], rows = padded rows + 8 (row `padded` stays zero)
@@ -876,14 +1169,16 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
     const int zero_row = (int)(A.shard_rows[partner] * A.shard_count);
     __half *const *peers = A.peer_n[which] > 0 ? reinterpret_cast<__half *const *>(A.peer_tab[which].p) : nullptr;
     const int n_peers = A.peer_n[which];
-    const size_t smem = (size_t)tc::Smem::total + 1024;
     const int64_t rows = re - rb;
     const int grid = (int)(rows < ctx->sm_count ? rows : ctx->sm_count);
     FMS_TRY(ensure_stage_csr(ctx, which, rb, re, zero_row, grid));
     // producer flavour: LDGSTS for short rows (see the kernel), TMA gather4 for long ones
     const int64_t n_side = which == 0 ? A.n_users : A.n_items;
-    const bool ldgsts = !dump && (A.kernel == FMS_ALS_KERNEL_TC_LDGSTS ||
-                                  (A.kernel != FMS_ALS_KERNEL_TC_TMA && n_side > 0 && A.nnz / n_side < 16 * tc::KROWS));
+    const bool short_rows = n_side > 0 && A.nnz / n_side < 16 * tc::KROWS;
+    const bool ldgsts = !dump && (A.kernel == FMS_ALS_KERNEL_TC_LDGSTS || (A.kernel != FMS_ALS_KERNEL_TC_TMA && short_rows));
+    static const bool use_v1 = getenv("FMS_ALS_TC_V1") != nullptr;             // A/B switch: the round-1 kernel (CUDA-core solver)
+    if (use_v1) {
+        const size_t smem = (size_t)tc::Smem::total + 1024;
 #define FMS_TC_LAUNCH(DUMPF, LDG, DUMP_PTR)                                                                                          \
     do {                                                                                                                             \
         FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<DUMPF, LDG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -891,10 +1186,28 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
             m_pl, A.ptr[which].p, A.stage_ptr[which].p, A.colp[which].p, A.valp[which].p, A.cta_rows[which].p, A.fac[which].p, t_hi,  \
             lambda, rb, A.info.p, DUMP_PTR, peers, n_peers, p_hi);                                                                   \
     } while (0)
-    if (dump) FMS_TC_LAUNCH(true, false, dump);
-    else if (ldgsts) FMS_TC_LAUNCH(false, true, nullptr);
-    else FMS_TC_LAUNCH(false, false, nullptr);
+        if (dump) FMS_TC_LAUNCH(true, false, dump);
+        else if (ldgsts) FMS_TC_LAUNCH(false, true, nullptr);
+        else FMS_TC_LAUNCH(false, false, nullptr);
 #undef FMS_TC_LAUNCH
+    } else {
+        // v2: ring depth / active solver warps per row-length regime (many short systems: 12 solver warps, 13 stages;
+        // few long ones: 6 solver warps, 26 stages of gathers in flight)
+#define FMS_TC2_LAUNCH(DUMPF, LDG, NS, NA, DUMP_PTR)                                                                                    \
+    do {                                                                                                                             \
+        const size_t smem = (size_t)tc::Smem2<NS, NA>::total + 1024;                                                                  \
+        FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64_v2<DUMPF, LDG, NS, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        tc::k_als_rows_tc64_v2<DUMPF, LDG, NS, NA><<<grid, tc::V2_WARPS * 32, smem, ctx->stream>>>(                                    \
+            m_pl, A.ptr[which].p, A.stage_ptr[which].p, A.colp[which].p, A.valp[which].p, A.cta_rows[which].p, A.fac[which].p, t_hi,  \
+            lambda, rb, A.info.p, DUMP_PTR, peers, n_peers, p_hi);                                                                   \
+    } while (0)
+        if (dump) FMS_TC2_LAUNCH(true, false, 13, 12, dump);
+        else if (short_rows && ldgsts) FMS_TC2_LAUNCH(false, true, 13, 12, nullptr);
+        else if (short_rows) FMS_TC2_LAUNCH(false, false, 13, 12, nullptr);
+        else if (ldgsts) FMS_TC2_LAUNCH(false, true, 26, 6, nullptr);
+        else FMS_TC2_LAUNCH(false, false, 26, 6, nullptr);
+#undef FMS_TC2_LAUNCH
+    }
     FMS_LAUNCH_CHECK(ctx);
     // the kernel wrote the planes of its own rows; with one shard that is the whole side
     A.plane_valid[which] = (A.shard_count == 1);

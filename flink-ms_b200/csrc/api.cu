@@ -228,6 +228,13 @@ FMS_API int fms_als_planes_open_peers(fms_ctx *ctx, int which, const void *handl
     return als_tc_open_peers(ctx, which, handles, n);
 }
 
+FMS_API int fms_als_planes_peer_count(fms_ctx *ctx, int which, int *n_peers) {
+    if (!ctx) return FMS_ERR_INVALID_ARG;
+    if ((which != 0 && which != 1) || !n_peers) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_planes_peer_count: bad arguments");
+    *n_peers = ctx->als.peer_n[which];
+    return FMS_OK;
+}
+
 FMS_API int fms_als_planes_updated(fms_ctx *ctx, int which) {
     if (!ctx) return FMS_ERR_INVALID_ARG;
     if (which != 0 && which != 1) return fail(ctx, FMS_ERR_INVALID_ARG, "which = %d", which);
@@ -247,7 +254,14 @@ FMS_API int fms_als_fit(fms_ctx *ctx, const int64_t *user, const int64_t *item, 
         FMS_TRY(fms_als_half_step(ctx, FMS_ITEMS, lambda));
     }
     FMS_TRY(fms_als_half_step(ctx, FMS_USERS, lambda));   // the extra user half-step after the loop
+    // dposv's info: FlinkML ignores it and so does the fit, but a model with broken-down rows (NaN factors: a system that
+    // is not positive definite, or |rating| / |factor| beyond what the kernel's operand format holds) must not leave
+    // silently -- the count stays readable through fms_als_last_info and the message through fms_last_error.
+    int bad = 0;
+    FMS_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->als.info.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
     FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad) fail(ctx, FMS_OK, "fms_als_fit: %d row(s) of the last half-step broke down (non-positive pivot, dposv info != 0)", bad);
+    else ctx->err.clear();
     return FMS_OK;
 }
 

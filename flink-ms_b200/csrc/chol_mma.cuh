@@ -1,0 +1,252 @@
+// chol_mma.cuh -- one warp solves one SPD system (A + lambda n I) x = b of order D = 16 MT on the warp-level tensor path
+// (mma.sync m16n8k8 TF32, SASS HMMA.1688.F32.TF32) with error-compensated 3xTF32 products.
+//
+// Why: the round-1 solver (one matrix row per lane, trailing updates as FFMA2 against broadcast LDS.128) was bound by the
+// shared-memory data pipe (ncu: l1tex data-pipe wavefronts 94 % of peak, 2 240 of them per 64x64 system) and by issue
+// slots (7 000 warp instructions per system for ~750 useful FFMA2).  A broadcast LDS delivers two floats per wavefront; an
+// MMA fragment holds its operands in registers, so the blocked factorisation below moves every tile through shared memory
+// once per panel and issues ~3 HMMA where the old code issued 16 FFMA2 + 8 LDS.128.
+//
+// Data layout ("tile layout"): the NEGATED system S = -(A + lambda n I) is stored as the 16x8 tiles (I, j), j <= 2 I + 1,
+// of its lower triangle (diagonal tiles complete), tile (I, j) at float offset 128 (I (I + 1) + j), each tile in
+// mma-accumulator order: lane (g = lane / 4, t = lane % 4) owns the float4
+//      ( S[16 I + g][8 j + 2 t], S[16 I + g][8 j + 2 t + 1], S[16 I + g + 8][8 j + 2 t], S[16 I + g + 8][8 j + 2 t + 1] ).
+// That is exactly what tcgen05.ld.16x256b hands the epilogue warps (tools/micro/mma_sync_rate.cu prints the mapping), and an
+// accumulator tile can be fed back as the A operand (rows) or the B operand (columns of a later tile) of the next MMA
+// without moving data when the k slots are read as k = t -> column 2 t, k = t + 4 -> column 2 t + 1.
+// The right-hand side travels as row D of the matrix (bz = -b): the panel loop then leaves z = L^-1 b in bz.
+//
+// Right-looking, panel width 8 (one n-tile):
+//   1. the 8x8 diagonal block is read by every lane (broadcast LDS.64) and factored redundantly in registers;
+//      every lane derives row g of W = Ld^-1, i.e. its B fragment of -W;
+//   2. "trsm" as a product: L(I, J) = S(I, J) (-W)^T for every m-tile of the panel (3 HMMA each);
+//   3. trailing update S(I, j) += L(I, J) L(j, J)^T for j > J (3 HMMA per tile, fragments straight from step 2);
+//   4. the same two steps for the right-hand-side row.
+// Back substitution is scalar (one column per lane and 32-column block, pivots in groups of four).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fms {
+namespace cm {
+
+// round to TF32 (10 explicit mantissa bits), ties away from zero: the same result as cvt.rna.tf32.f32 for finite inputs in two
+// integer instructions (sm_100a emulates the cvt with FSETP + IMAD + LOP3; the tensor core ignores the low 13 bits anyway, the
+// mask only keeps `x - hi` exact).  Inf / NaN stay non-finite.
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+// x ~= hi + lo with hi, lo representable in TF32 (22 mantissa bits together)
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float4 &c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c.x), "+f"(c.y), "+f"(c.z), "+f"(c.w)
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// A operand from an accumulator-layout tile: rows g / g + 8, k slot t = column 2 t, k slot t + 4 = column 2 t + 1
+struct AFrag {
+    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+    __device__ __forceinline__ void set(float x, float y, float z, float w) {   // (row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)
+        split_tf32(x, h0, l0); split_tf32(z, h1, l1); split_tf32(y, h2, l2); split_tf32(w, h3, l3);
+    }
+};
+// c += A B^T with 3xTF32: hi hi + hi lo + lo hi (the small terms first)
+__device__ __forceinline__ void mma3(float4 &c, const AFrag &a, uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+    mma_tf32(c, a.l0, a.l1, a.l2, a.l3, bh0, bh1);
+    mma_tf32(c, a.h0, a.h1, a.h2, a.h3, bl0, bl1);
+    mma_tf32(c, a.h0, a.h1, a.h2, a.h3, bh0, bh1);
+}
+
+__device__ __forceinline__ float rsqrt_nr(float x) {
+    const float r = rsqrtf(x);
+    return r * fmaf(-0.5f * x * r, r, 1.5f);              // one Newton step: ~1 ulp; a non-positive pivot becomes NaN
+}
+__device__ __forceinline__ float sel4(int t, float a, float b, float c, float d) {
+    const float lo = (t & 1) ? b : a, hi = (t & 1) ? d : c;
+    return (t & 2) ? hi : lo;
+}
+
+template <int MT>
+struct Tiles {
+    static constexpr int D = 16 * MT, NT = 2 * MT;
+    static constexpr int N_TILES = MT * (MT + 1);
+    static constexpr int FLOATS = N_TILES * 128;
+    __host__ __device__ static constexpr int off(int I, int j) { return (I * (I + 1) + j) * 128; }
+    // float offset of element (k, i), k >= i
+    __host__ __device__ static constexpr int at(int k, int i) {
+        return off(k >> 4, i >> 3) + ((k & 7) * 4 + ((i & 7) >> 1)) * 4 + ((k >> 3) & 1) * 2 + (i & 1);
+    }
+};
+
+// Solves one system in place.  S: tile layout (negated matrix) -- holds L afterwards.  bz: D floats, -b in, z out.
+// invd: D floats scratch (1 / L_jj).  xs: D floats scratch (x, for the broadcasts of the back substitution).
+// x_out[q] = x[lane + 32 q].  All four arrays are private to the calling warp; the caller provides the barrier that
+// made S and bz visible (mbarrier wait or __syncwarp).
+template <int MT>
+__device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__restrict__ bz, float *__restrict__ invd, float *__restrict__ xs,
+                                            const int lane, float (&x_out)[MT / 2]) {
+    using TL = Tiles<MT>;
+    constexpr int D = TL::D, NT = TL::NT;
+    const int g = lane >> 2, t = lane & 3;
+    float4 *S4 = reinterpret_cast<float4 *>(S);
+    uint32_t bh0[NT], bh1[NT], bl0[NT], bl1[NT];            // B fragments (hi / lo) of the current panel's L, per n-tile
+#pragma unroll
+    for (int j = 0; j < NT; ++j) bh0[j] = bh1[j] = bl0[j] = bl1[j] = 0u;
+
+#pragma unroll 1
+    for (int J = 0; J < NT; ++J) {
+        const int Id = J >> 1, h = J & 1;
+        // ---- 1. diagonal block, factored redundantly: a[r (r + 1) / 2 + c] = (A + lambda n I)[8 J + r][8 J + c], c <= r
+        uint32_t wb_h0, wb_h1, wb_l0, wb_l1;
+        {
+            const float *Td = S + (Id * (Id + 1) + J) * 128 + 2 * h;
+            float a[36];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int cp = 0; 2 * cp <= r; ++cp) {
+                    const float2 v = *reinterpret_cast<const float2 *>(Td + (4 * r + cp) * 4);
+                    a[r * (r + 1) / 2 + 2 * cp] = -v.x;
+                    if (2 * cp + 1 <= r) a[r * (r + 1) / 2 + 2 * cp + 1] = -v.y;
+                }
+            float rinv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                rinv[k] = rsqrt_nr(a[k * (k + 1) / 2 + k]);
+#pragma unroll
+                for (int i = k + 1; i < 8; ++i) a[i * (i + 1) / 2 + k] *= rinv[k];
+#pragma unroll
+                for (int j = k + 1; j < 8; ++j)
+#pragma unroll
+                    for (int i = j; i < 8; ++i) a[i * (i + 1) / 2 + j] = fmaf(-a[i * (i + 1) / 2 + k], a[j * (j + 1) / 2 + k], a[i * (i + 1) / 2 + j]);
+            }
+            if (lane == 0) {
+                *reinterpret_cast<float4 *>(invd + 8 * J) = make_float4(rinv[0], rinv[1], rinv[2], rinv[3]);
+                *reinterpret_cast<float4 *>(invd + 8 * J + 4) = make_float4(rinv[4], rinv[5], rinv[6], rinv[7]);
+            }
+            // row g of W = Ld^-1 (w Ld = e_g^T, solved from the right; entries right of the diagonal come out 0)
+            float wv[8];
+#pragma unroll
+            for (int c = 7; c >= 0; --c) {
+                float s = (c == g) ? 1.f : 0.f;
+#pragma unroll
+                for (int m = c + 1; m < 8; ++m) s = fmaf(-wv[m], a[m * (m + 1) / 2 + c], s);
+                wv[c] = s * rinv[c];
+            }
+            // B fragment of -W: n = g (row of W), k slot t -> column 2 t, k slot t + 4 -> column 2 t + 1
+            split_tf32(-sel4(t, wv[0], wv[2], wv[4], wv[6]), wb_h0, wb_l0);
+            split_tf32(-sel4(t, wv[1], wv[3], wv[5], wv[7]), wb_h1, wb_l1);
+        }
+        // ---- 2 + 3. panel tiles: L(I, J) = S(I, J) (-W)^T, then S(I, j) += L(I, J) L(j, J)^T for J < j <= 2 I + 1
+#pragma unroll
+        for (int I = 0; I < MT; ++I) {
+            if (I >= Id) {
+                const float4 sv = S4[(I * (I + 1) + J) * 32 + lane];
+                AFrag af;
+                af.set(sv.x, sv.y, sv.z, sv.w);
+                float4 L = make_float4(0.f, 0.f, 0.f, 0.f);
+                mma3(L, af, wb_h0, wb_h1, wb_l0, wb_l1);
+                if (I == Id) {
+                    // rows of the diagonal block: keep the lower triangle (the product reproduces Ld up to rounding noise
+                    // above the diagonal); rows of the m-tile above the block belong to finished panels: zero
+                    const bool u0 = 2 * t > g, u1 = 2 * t + 1 > g;
+                    if (h == 0) { L.x = u0 ? 0.f : L.x; L.y = u1 ? 0.f : L.y; }
+                    else { L.x = 0.f; L.y = 0.f; L.z = u0 ? 0.f : L.z; L.w = u1 ? 0.f : L.w; }
+                }
+                S4[(I * (I + 1) + J) * 32 + lane] = L;
+                af.set(L.x, L.y, L.z, L.w);
+                bh0[2 * I] = af.h0; bh1[2 * I] = af.h2; bl0[2 * I] = af.l0; bl1[2 * I] = af.l2;                  // rows g     -> n-tile 2 I
+                bh0[2 * I + 1] = af.h1; bh1[2 * I + 1] = af.h3; bl0[2 * I + 1] = af.l1; bl1[2 * I + 1] = af.l3;  // rows g + 8 -> n-tile 2 I + 1
+#pragma unroll
+                for (int j = 0; j <= 2 * I + 1; ++j) {
+                    if (j > J) {
+                        float4 c = S4[(I * (I + 1) + j) * 32 + lane];
+                        mma3(c, af, bh0[j], bh1[j], bl0[j], bl1[j]);
+                        S4[(I * (I + 1) + j) * 32 + lane] = c;
+                    }
+                }
+            }
+        }
+        // ---- 4. right-hand-side row (row D of the matrix): z_J = bz_J (-W)^T, bz_j += z_J L(j, J)^T
+        {
+            float2 bv = make_float2(0.f, 0.f);
+            if (g == 0) bv = *reinterpret_cast<const float2 *>(bz + 8 * J + 2 * t);
+            AFrag af;
+            af.h1 = af.h3 = af.l1 = af.l3 = 0u;
+            split_tf32(bv.x, af.h0, af.l0);
+            split_tf32(bv.y, af.h2, af.l2);
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            mma3(z, af, wb_h0, wb_h1, wb_l0, wb_l1);
+            if (g == 0) *reinterpret_cast<float2 *>(bz + 8 * J + 2 * t) = make_float2(z.x, z.y);
+            split_tf32(z.x, af.h0, af.l0);
+            split_tf32(z.y, af.h2, af.l2);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                if (j > J) {
+                    float2 cv = make_float2(0.f, 0.f);
+                    if (g == 0) cv = *reinterpret_cast<const float2 *>(bz + 8 * j + 2 * t);
+                    float4 c = make_float4(cv.x, cv.y, 0.f, 0.f);
+                    mma3(c, af, bh0[j], bh1[j], bl0[j], bl1[j]);
+                    if (g == 0) *reinterpret_cast<float2 *>(bz + 8 * j + 2 * t) = make_float2(c.x, c.y);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- back substitution L^T x = z: column i = lane + 32 q per lane, pivots in groups of four, blocks of 32 columns descending
+    constexpr int NQ = MT / 2;
+    float zq[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) zq[q] = bz[lane + 32 * q];
+    const int lp = (lane >> 3) * 128 + ((lane & 7) >> 1) * 4 + (lane & 1);      // lane part of Tiles::at(k, 32 q + lane)
+#pragma unroll
+    for (int q = NQ - 1; q >= 0; --q) {
+        float x = 0.f;
+#pragma unroll 1
+        for (int jr = 28; jr >= 0; jr -= 4) {
+            const int j0 = 32 * q + jr;
+            const float z0 = __shfl_sync(0xffffffffu, zq[q], jr), z1 = __shfl_sync(0xffffffffu, zq[q], jr + 1);
+            const float z2 = __shfl_sync(0xffffffffu, zq[q], jr + 2), z3 = __shfl_sync(0xffffffffu, zq[q], jr + 3);
+            // rows j0 .. j0 + 3 share m-tile and half; element (j0 + r, i) at rb + 16 r + (column part)
+            const int I = j0 >> 4;
+            const int rb = (I * (I + 1)) * 128 + (j0 & 7) * 16 + ((j0 >> 3) & 1) * 2;
+            const int cb = rb + (j0 >> 3) * 128 + ((j0 & 7) >> 1) * 4;                  // column j0 (even): columns j0 + c at + (c >> 1) * 4 + (c & 1)
+            const float l10 = S[cb + 16], l20 = S[cb + 32], l21 = S[cb + 32 + 1], l30 = S[cb + 48], l31 = S[cb + 48 + 1], l32 = S[cb + 48 + 4];
+            const float4 iv = *reinterpret_cast<const float4 *>(invd + j0);
+            const float v3 = z3 * iv.w;
+            const float v2 = fmaf(-l32, v3, z2) * iv.z;
+            const float v1 = fmaf(-l31, v3, fmaf(-l21, v2, z1)) * iv.y;
+            const float v0 = fmaf(-l30, v3, fmaf(-l20, v2, fmaf(-l10, v1, z0))) * iv.x;
+            const int rel = lane - jr;
+            if (rel >= 0 && rel < 4) x = sel4(rel, v0, v1, v2, v3);
+            if (rel < 0) {                                            // columns left of the group: z_i -= sum_c L[j0 + c][i] x_c
+                const float *p = S + rb + 4 * q * 128 + lp;
+                zq[q] = fmaf(-p[48], v3, fmaf(-p[32], v2, fmaf(-p[16], v1, fmaf(-p[0], v0, zq[q]))));
+            }
+        }
+        x_out[q] = x;
+        if (q > 0) {
+            xs[32 * q + lane] = x;
+            __syncwarp();
+            // earlier column blocks: z_i -= sum_{k in block q} L[k][i] x_k
+#pragma unroll
+            for (int q2 = 0; q2 < q; ++q2) {
+                float acc = zq[q2];
+#pragma unroll 1
+                for (int k4 = 0; k4 < 32; k4 += 4) {
+                    const int k = 32 * q + k4;
+                    const int I = k >> 4;
+                    const float *p = S + (I * (I + 1) + 4 * q2) * 128 + (k & 7) * 16 + ((k >> 3) & 1) * 2 + lp;
+                    const float4 xv = *reinterpret_cast<const float4 *>(xs + k);
+                    acc = fmaf(-p[48], xv.w, fmaf(-p[32], xv.z, fmaf(-p[16], xv.y, fmaf(-p[0], xv.x, acc))));
+                }
+                zq[q2] = acc;
+            }
+        }
+    }
+}
+
+}  // namespace cm
+}  // namespace fms

@@ -80,41 +80,47 @@ class ContextALSBackend:
     def updated(self, which):
         self.ctx.als_factors_updated(which)
 
+    def _planes_supported(self):
+        """False when the tensor-core path (and so the gather planes) does not cover this ctx's rank: the one
+        condition under which falling back to the NCCL all-gather is legitimate.  Every other error propagates."""
+        from ._native import ERR_UNSUPPORTED, FlinkMSError
+        try:
+            self.ctx.als_planes_device(0)
+        except FlinkMSError as e:
+            if e.status != ERR_UNSUPPORTED:
+                raise
+            return False
+        return True
+
     def enable_p2p(self, group=None):
         """Map every rank's gather planes into this process (CUDA IPC) so that the half-step kernel writes its plane rows
-        into all replicas itself.  Returns False when the tensor-core path (and so the planes) is not in use."""
+        into all replicas itself.  Returns False only when the tensor-core path (and so the planes) is not in use on some
+        rank; a failing IPC exchange raises.  The mappings belong to the ctx's plane buffers: when they are already in
+        place for this world size (same geometry re-loaded) nothing is exchanged again."""
         world = dist.get_world_size(group)
-        try:
-            for which in (0, 1):
-                mine = self.ctx.als_planes_ipc_handle(which)
-                handles = [None] * world
-                dist.all_gather_object(handles, mine, group=group)
-                self.ctx.als_planes_open_peers(which, b"".join(handles), world)
-        except Exception:  # noqa: BLE001  (FMS_ERR_UNSUPPORTED: generic kernel in use; IPC not available)
-            for which in (0, 1):
-                try:
-                    self.ctx.als_planes_open_peers(which, b"", 0)
-                except Exception:  # noqa: BLE001
-                    pass
-            self.p2p = False
-            ok = torch.zeros(1, device=self.device)
-        else:
-            self.p2p = True
-            ok = torch.ones(1, device=self.device)
+        ok = torch.tensor([1.0 if self._planes_supported() else 0.0], device=self.device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)           # all ranks or none
-        if ok.item() == 0 and self.p2p:
-            for which in (0, 1):
-                self.ctx.als_planes_open_peers(which, b"", 0)
+        if ok.item() == 0:
             self.p2p = False
-        return self.p2p
+            return False
+        mapped = torch.tensor([1.0 if all(self.ctx.als_planes_peer_count(w) == world for w in (0, 1)) else 0.0], device=self.device)
+        dist.all_reduce(mapped, op=dist.ReduceOp.MIN, group=group)
+        if mapped.item() == 0:
+            mine = torch.frombuffer(bytearray(self.ctx.als_planes_ipc_handle(0) + self.ctx.als_planes_ipc_handle(1)), dtype=torch.uint8).to(self.device)
+            table = torch.empty(world * 128, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(table, mine, group=group)        # one 128-byte all-gather, no pickling
+            table = table.cpu().numpy().reshape(world, 2, 64)
+            for which in (0, 1):
+                self.ctx.als_planes_open_peers(which, table[:, which, :].tobytes(), world)
+        self.p2p = True
+        return True
 
     def plane_tensors(self, which, rank):
         """fp16 views of the gather planes as a tuple of tensors to all-gather, or None when the tensor-core path does
         not cover `rank`.  The planes are interleaved (one row = rank hi halves then rank lo halves), i.e. ONE tensor."""
-        try:
-            hi, _lo, rows = self.ctx.als_planes_device(which)
-        except Exception:  # noqa: BLE001  (FMS_ERR_UNSUPPORTED: generic kernel in use)
+        if not self._planes_supported():
             return None
+        hi, _lo, rows = self.ctx.als_planes_device(which)
         return (device_view(hi, rows * 2 * rank, torch.float16, self.device).view(rows, 2 * rank),)
 
     def planes_updated(self, which):

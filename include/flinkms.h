@@ -168,6 +168,9 @@ FMS_API int fms_als_planes_device(fms_ctx *ctx, int which, void **hi, void **lo,
 FMS_API int fms_als_planes_ipc_handle(fms_ctx *ctx, int which, void *handle64);
 FMS_API int fms_als_planes_open_peers(fms_ctx *ctx, int which, const void *handles, int n);
 FMS_API int fms_als_planes_updated(fms_ctx *ctx, int which);
+/* number of replicas currently mapped for a side (0 = none): lets a host skip the handle exchange when the mappings of
+ * an earlier fit are still valid (same plane buffers, same world size) */
+FMS_API int fms_als_planes_peer_count(fms_ctx *ctx, int which, int *n_peers);
 /* number of rows whose Cholesky hit a non-positive pivot in the last half-step (dposv info != 0; FlinkML
  * ignores it, so do we -- exposed for tests). */
 FMS_API int fms_als_last_info(fms_ctx *ctx, int64_t *bad_rows);
