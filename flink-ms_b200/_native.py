@@ -117,11 +117,18 @@ def _f64(a):
 class Context:
     """One fms_ctx: one GPU, one stream.  Not thread-safe (like the reference's per-thread helpers)."""
 
-    def __init__(self, device: int | None = None):
+    def __init__(self, device: int | None = None, devices=None):
+        """device: one GPU (None = current).  devices=[d0, d1, ...]: a GROUP ctx -- this one process drives all of them through
+        the whole-fit entry points (als_fit, svm_fit; model read-out and predict are served by d0); see include/flinkms.h."""
         self._lib = load()
         self._h = _vp()
-        ids = None if device is None else (C.c_int * 1)(device)
-        rc = self._lib.fms_create(C.byref(self._h), ids, 1)
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            ids, n = (C.c_int * len(devices))(*devices), len(devices)
+        else:
+            ids, n = (None if device is None else (C.c_int * 1)(device)), 1
+        self.n_devices = n
+        rc = self._lib.fms_create(C.byref(self._h), ids, n)
         if rc != OK:
             raise FlinkMSError(rc, (self._lib.fms_last_error(None) or b"").decode())
 

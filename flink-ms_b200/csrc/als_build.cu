@@ -5,6 +5,8 @@
 // distinct ids, and the ratings are regrouped by target row with the partner index ascending inside a
 // row (duplicate (u,i) pairs stay separate ratings in input order, as a DataSet would keep them).
 // One-off integer sort/scan work (CUB radix sort) -- not part of the per-iteration hot loop.
+#include <algorithm>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -28,6 +30,16 @@ __global__ void k_make_keys(const int32_t *__restrict__ row, const int32_t *__re
                             uint64_t *__restrict__ keys) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k < n) keys[k] = ((uint64_t)(uint32_t)row[k] << 32) | (uint32_t)colv[k];
+}
+// sharded build: flag the ratings whose row this rank solves
+__global__ void k_make_keys_flags(const int32_t *__restrict__ row, const int32_t *__restrict__ colv, int64_t n, int32_t rb, int32_t re,
+                                  uint64_t *__restrict__ keys, uint8_t *__restrict__ flags) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) {
+        const int32_t r = row[k];
+        keys[k] = ((uint64_t)(uint32_t)r << 32) | (uint32_t)colv[k];
+        flags[k] = (r >= rb && r < re) ? 1 : 0;
+    }
 }
 
 __global__ void k_f64_to_f32(const double *__restrict__ in, int64_t n, float *__restrict__ out) {
@@ -86,18 +98,50 @@ static int unique_ids(fms_ctx *ctx, const int64_t *d_raw, int64_t n, DevBuf<int6
     return FMS_OK;
 }
 
+// rb / re: the rows this rank solves.  With more than one shard only THEIR ratings are sorted into the CSR (rows outside
+// get empty ranges): SURVEY.md 8(e) "rank g holds the by-user CSR for its users and the by-item CSR for its items" -- the
+// replicated build was what kept the end-to-end time from scaling in round 1.
 static int build_side(fms_ctx *ctx, int side, const int32_t *d_row, const int32_t *d_col, const float *d_val, int64_t nnz,
                       int64_t n_rows, int64_t n_cols, DevBuf<uint64_t> &keys_in, DevBuf<uint64_t> &keys_out,
-                      DevBuf<unsigned char> &temp) {
+                      DevBuf<unsigned char> &temp, int64_t rb, int64_t re) {
     AlsState &A = ctx->als;
     cudaStream_t st = ctx->stream;
     const int T = 256;
     FMS_CUDA(ctx, A.ptr[side].alloc((size_t)n_rows + 1));
-    FMS_CUDA(ctx, A.col[side].alloc((size_t)nnz));
-    FMS_CUDA(ctx, A.val[side].alloc((size_t)nnz));
-    if (nnz > 0) {
-        k_make_keys<<<grid_for(nnz, T), T, 0, st>>>(d_row, d_col, nnz, keys_in.p);
+    DevBuf<float> val_sel;
+    if (nnz > 0 && (rb > 0 || re < n_rows)) {
+        DevBuf<uint8_t> flags;
+        DevBuf<int64_t> d_cnt;
+        FMS_CUDA(ctx, flags.alloc((size_t)nnz));
+        FMS_CUDA(ctx, d_cnt.alloc(1));
+        FMS_CUDA(ctx, val_sel.alloc((size_t)nnz));
+        k_make_keys_flags<<<grid_for(nnz, T), T, 0, st>>>(d_row, d_col, nnz, (int32_t)rb, (int32_t)re, keys_out.p, flags.p);
         FMS_LAUNCH_CHECK(ctx);
+        size_t tb = 0, tb2 = 0;
+        FMS_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, tb, keys_out.p, flags.p, keys_in.p, d_cnt.p, nnz, st));
+        FMS_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, tb2, d_val, flags.p, val_sel.p, d_cnt.p, nnz, st));
+        FMS_CUDA(ctx, temp.alloc(tb > tb2 ? tb : tb2));
+        size_t t = temp.n;
+        FMS_CUDA(ctx, cub::DeviceSelect::Flagged(temp.p, t, keys_out.p, flags.p, keys_in.p, d_cnt.p, nnz, st));
+        t = temp.n;
+        FMS_CUDA(ctx, cub::DeviceSelect::Flagged(temp.p, t, d_val, flags.p, val_sel.p, d_cnt.p, nnz, st));
+        ctx->launches += 2;
+        int64_t h = 0;
+        FMS_CUDA(ctx, cudaMemcpyAsync(&h, d_cnt.p, sizeof h, cudaMemcpyDeviceToHost, st));
+        FMS_CUDA(ctx, cudaStreamSynchronize(st));
+        nnz = h;
+        d_val = val_sel.p;
+        FMS_CUDA(ctx, A.col[side].alloc((size_t)nnz));
+        FMS_CUDA(ctx, A.val[side].alloc((size_t)nnz));
+    } else {
+        FMS_CUDA(ctx, A.col[side].alloc((size_t)nnz));
+        FMS_CUDA(ctx, A.val[side].alloc((size_t)nnz));
+        if (nnz > 0) {
+            k_make_keys<<<grid_for(nnz, T), T, 0, st>>>(d_row, d_col, nnz, keys_in.p);
+            FMS_LAUNCH_CHECK(ctx);
+        }
+    }
+    if (nnz > 0) {
         const int end_bit = 32 + bits_for(n_rows);
         size_t tb = 0;
         FMS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in.p, keys_out.p, d_val, A.val[side].p, nnz, 0,
@@ -117,7 +161,8 @@ static int build_side(fms_ctx *ctx, int side, const int32_t *d_row, const int32_
 }
 
 // h_user / h_item / h_rating: host OR device pointers (unified addressing decides the copy direction)
-int als_build_csr(fms_ctx *ctx, const int64_t *h_user, const int64_t *h_item, const double *h_rating, int64_t nnz) {
+int als_build_csr(fms_ctx *ctx, const int64_t *h_user, const int64_t *h_item, const double *h_rating, int64_t nnz, int shard_index,
+                  int shard_count) {
     AlsState &A = ctx->als;
     cudaStream_t st = ctx->stream;
     const int T = 256;
@@ -166,8 +211,11 @@ int als_build_csr(fms_ctx *ctx, const int64_t *h_user, const int64_t *h_item, co
     d_item.release();
     FMS_CUDA(ctx, keys_in.alloc((size_t)nnz));
     FMS_CUDA(ctx, keys_out.alloc((size_t)nnz));
-    FMS_TRY(build_side(ctx, 0, du.p, di.p, d_r32.p, nnz, nu, ni, keys_in, keys_out, temp));
-    FMS_TRY(build_side(ctx, 1, di.p, du.p, d_r32.p, nnz, ni, nu, keys_in, keys_out, temp));
+    const int64_t su = (nu + shard_count - 1) / shard_count, si = (ni + shard_count - 1) / shard_count;
+    const int64_t ub = std::min<int64_t>(nu, su * shard_index), ue = std::min<int64_t>(nu, su * (shard_index + 1));
+    const int64_t ib = std::min<int64_t>(ni, si * shard_index), ie = std::min<int64_t>(ni, si * (shard_index + 1));
+    FMS_TRY(build_side(ctx, 0, du.p, di.p, d_r32.p, nnz, nu, ni, keys_in, keys_out, temp, ub, ue));
+    FMS_TRY(build_side(ctx, 1, di.p, du.p, d_r32.p, nnz, ni, nu, keys_in, keys_out, temp, ib, ie));
     FMS_CUDA(ctx, cudaStreamSynchronize(st));
     return FMS_OK;
 }

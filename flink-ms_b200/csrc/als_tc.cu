@@ -174,6 +174,41 @@ __device__ __forceinline__ void tc_stage_mma(uint32_t d, uint32_t lo_hi, uint32_
         : "memory");
 }
 
+// v2: one 16-rating sub-stage of a ring slot.  commit_empty: last sub-stage of the slot (releases it to the producers);
+// last: last sub-stage of the row (hands the accumulator to the epilogue); n_mma: 2 (0 / 1 only in timing experiments).
+__device__ __forceinline__ void tc_stage_mma2(uint32_t d, uint32_t lo_hi, uint32_t lo_lo, uint32_t lo_b2, uint32_t idesc_n1, uint32_t idesc_n2,
+                                              uint32_t accumulate, uint32_t bar_empty, uint32_t bar_acc, uint32_t commit_empty, uint32_t last,
+                                              uint32_t n_mma) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pa, pl, pt, pc, p1, p2;\n"
+        ".reg .b32 d2;\n"
+        ".reg .b64 ahi, alo, b2;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pa, %6, 0;\n"
+        "setp.ne.b32 pt, %10, 0;\n"
+        "and.pred pl, pt, pe;\n"
+        "setp.ne.b32 pt, %9, 0;\n"
+        "and.pred pc, pt, pe;\n"
+        "setp.ge.u32 pt, %11, 1;\n"
+        "and.pred p1, pt, pe;\n"
+        "setp.ge.u32 pt, %11, 2;\n"
+        "and.pred p2, pt, pe;\n"
+        "setp.eq.u32 pt, %0, %0;\n"
+        "add.u32 d2, %0, 64;\n"
+        "mov.b64 ahi, {%1, 0x40004040};\n"
+        "mov.b64 alo, {%2, 0x40004040};\n"
+        "mov.b64 b2, {%3, 0x40004040};\n"
+        "@p1 tcgen05.mma.cta_group::1.kind::f16 [%0], ahi, ahi, %4, pa;\n"
+        "@p2 tcgen05.mma.cta_group::1.kind::f16 [d2], alo, b2, %5, pt;\n"
+        "@pc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
+        "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n"
+        "}\n" ::"r"(d),
+        "r"(lo_hi), "r"(lo_lo), "r"(lo_b2), "r"(idesc_n1), "r"(idesc_n2), "r"(accumulate), "r"(bar_empty), "r"(bar_acc), "r"(commit_empty),
+        "r"(last), "r"(n_mma)
+        : "memory");
+}
+
 // 32 lanes x 32 columns of 32-bit: thread i of the warp reads TMEM lane (quadrant base + i), columns [c, c+32)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -726,10 +761,10 @@ constexpr int V2_REGS_EPI = 72, V2_REGS_SOLVE = 104, V2_REGS_AUX = 40;     // (4
 using TL4 = cm::Tiles<4>;
 constexpr int V2_BUF_FLOATS = TL4::FLOATS + 3 * D;                          // tiles | bz | invd | xs  per solver warp
 
-template <int NSTG_, int NSA>
+template <int NSTG_, int NSA, int KS>
 struct Smem2 {
     static constexpr int ring = 0;
-    static constexpr int bufs = ring + NSTG_ * STAGE_BYTES;
+    static constexpr int bufs = ring + NSTG_ * KS * STAGE_BYTES;
     static constexpr int bars = bufs + NSA * V2_BUF_FLOATS * 4;
     static constexpr int n_bars = 2 * NSTG_ + 2 * NACC + 2 * NSA;
     static constexpr int tmem_ptr = bars + n_bars * 8;
@@ -755,14 +790,19 @@ __device__ __forceinline__ void tc_ld16x256_x1(uint32_t taddr, float (&v)[4]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <bool DUMP, bool LDGSTS, int NSTG_, int NSA>
+template <bool DUMP, bool LDGSTS, int NSTG_, int NSA, int KS, int NP>
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64_v2(
     const __grid_constant__ CUtensorMap map_pl, const int64_t *__restrict__ ptr,
     const int32_t *__restrict__ stage_ptr, const int32_t *__restrict__ colp, const float *__restrict__ valp,
     const int32_t *__restrict__ cta_rows, float *__restrict__ T, __half *__restrict__ T_pl, float lambda,
     int64_t row_begin, int *__restrict__ info, float *__restrict__ dump, __half *const *__restrict__ peers, int n_peers,
-    const __half *__restrict__ S_pl) {
-    using SM = Smem2<NSTG_, NSA>;
+    const __half *__restrict__ S_pl, int dbg) {
+    using SM = Smem2<NSTG_, NSA, KS>;
+    // Parity waits tell adjacent phases apart only: a producer may run at most one ring revolution ahead of the issuer.  Its
+    // previous stage was NP stages back and legitimately within NSTG_ of the issuer, so NSTG_ >= NP keeps it inside two
+    // phases (with 6 slots and 7 producers the seventh stage's producer passed its wait two phases early: mbarrier overflow).
+    static_assert(NSTG_ >= NP && NP <= N_PROD, "ring depth must cover the active producers");
+    constexpr int STG = KS * STAGE_BYTES;                       // one ring slot: KS sub-stages of 16 ratings (one handshake per slot)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
     const uint32_t sm_base = smem_u32(sm);
@@ -777,7 +817,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64_v2(
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sm + SM::tmem_ptr);
 
     // zero the ring once: the R / R' chunks only ever get their first four bytes per row rewritten
-    for (int i = threadIdx.x; i < NSTG_ * STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(sm + SM::ring)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < NSTG_ * STG / 16; i += blockDim.x) reinterpret_cast<uint4 *>(sm + SM::ring)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTG_; ++s) { mbar_init(bar_full(s), LDGSTS ? 33 : 1); mbar_init(bar_empty(s), 1); }
         for (int a = 0; a < NACC; ++a) { mbar_init(bar_acc_full(a), 1); mbar_init(bar_acc_empty(a), N_EPI); }
@@ -798,76 +838,86 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64_v2(
     if (warp >= V2_W_MMA) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V2_REGS_AUX));
       if (warp >= V2_W_PROD0) {
-        // ================================================================== producers (unchanged from v1)
+        // ================================================================== producers: one ring slot = KS sub-stages of 16 ratings
+        // (round 2: the mbarrier handshake per slot, not the gathers or the MMAs, paced the kernel -- with every MMA and every
+        // gather switched off it still needed ~280 cycles per 16-rating stage -- so a slot now carries KS x 16 ratings)
         const uint32_t pw = (uint32_t)(warp - V2_W_PROD0);
         const int64_t s_lo = stage_ptr[first], s_hi = stage_ptr[last];
-        const uint32_t n_local = (uint32_t)(s_hi - s_lo);
-        const int32_t *cp = colp + s_lo * KROWS + (lane & 15);
-        const float *vp = valp + s_lo * KROWS + (lane & 15);
-        int idx0 = 0, idx1 = 0;
-        float rt0 = 0.f, rt1 = 0.f;
-        if (pw < n_local) { idx0 = cp[(int64_t)pw * KROWS]; rt0 = vp[(int64_t)pw * KROWS]; }
-        if (pw + N_PROD < n_local) { idx1 = cp[(int64_t)(pw + N_PROD) * KROWS]; rt1 = vp[(int64_t)(pw + N_PROD) * KROWS]; }
-        for (uint32_t c = pw; c < n_local; c += N_PROD) {
-            int idx2 = 0;
-            float rt2 = 0.f;
-            if (c + 2 * N_PROD < n_local) { idx2 = cp[(int64_t)(c + 2 * N_PROD) * KROWS]; rt2 = vp[(int64_t)(c + 2 * N_PROD) * KROWS]; }
+        const uint32_t n_local = pw < (uint32_t)NP ? (uint32_t)(s_hi - s_lo) : 0u;      // producers beyond NP stay idle
+        const int32_t *cp = colp + s_lo * (KROWS * KS) + (lane & 15);
+        const float *vp = valp + s_lo * (KROWS * KS) + (lane & 15);
+        int idx0[KS], idx1[KS];
+        float rt0[KS], rt1[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            idx0[ks] = 0; rt0[ks] = 0.f;
+            if (pw < n_local) { idx0[ks] = cp[((int64_t)pw * KS + ks) * KROWS]; rt0[ks] = vp[((int64_t)pw * KS + ks) * KROWS]; }
+        }
+        for (uint32_t c = pw; c < n_local; c += NP) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                idx1[ks] = 0; rt1[ks] = 0.f;
+                if (c + NP < n_local) { idx1[ks] = cp[((int64_t)(c + NP) * KS + ks) * KROWS]; rt1[ks] = vp[((int64_t)(c + NP) * KS + ks) * KROWS]; }
+            }
             const int slot = c % NSTG_;
-            const uint32_t stage = sm_base + SM::ring + slot * STAGE_BYTES;
+            const uint32_t stage0 = sm_base + SM::ring + slot * STG;
+            unsigned char *stage0_p = sm + SM::ring + slot * STG;
+            mbar_wait(bar_empty(slot), ((c / NSTG_) & 1) ^ 1);
+            // ratings: R row r = (r_hi, r_lo * 2^11, 0...), R' row r = (0, r_hi, 0...); 16-byte chunk 0 sits at chunk (r & 7)
+            if (lane < 16) {
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    __half rh, rl;
+                    split_half(rt0[ks], rh, rl);
+                    const uint32_t off = (uint32_t)lane * 128u + (((uint32_t)lane & 7u) << 4);
+                    const uint32_t w0 = (uint32_t)__half_as_ushort(rh) | ((uint32_t)__half_as_ushort(rl) << 16);
+                    const uint32_t w1 = (uint32_t)__half_as_ushort(rh) << 16;
+                    *reinterpret_cast<uint32_t *>(stage0_p + ks * STAGE_BYTES + 2 * TILE_BYTES + off) = w0;
+                    *reinterpret_cast<uint32_t *>(stage0_p + ks * STAGE_BYTES + 2 * TILE_BYTES + (off ^ 16u)) = w1;
+                }
+            }
             if (LDGSTS) {
+                // lane l moves chunk (l & 7) of rows (l >> 3) + 4 k of both halves of the plane row into the 128B-swizzled tile
                 const int rq = lane >> 3, jc = lane & 7;
-                int ri[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ri[k] = __shfl_sync(0xffffffffu, idx0, 4 * k + rq);
-                mbar_wait(bar_empty(slot), ((c / NSTG_) & 1) ^ 1);
-                if (lane < 16) {
-                    __half rh, rl;
-                    split_half(rt0, rh, rl);
-                    const uint32_t off = (uint32_t)lane * 128u + (((uint32_t)lane & 7u) << 4);
-                    const uint32_t w0 = (uint32_t)__half_as_ushort(rh) | ((uint32_t)__half_as_ushort(rl) << 16);
-                    const uint32_t w1 = (uint32_t)__half_as_ushort(rh) << 16;
-                    *reinterpret_cast<uint32_t *>(sm + SM::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + off) = w0;
-                    *reinterpret_cast<uint32_t *>(sm + SM::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + (off ^ 16u)) = w1;
-                }
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint32_t stage = stage0 + ks * STAGE_BYTES;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int r = 4 * k + rq;
-                    const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((jc ^ (r & 7)) << 4);
-                    const char *src = reinterpret_cast<const char *>(S_pl) + (size_t)ri[k] * (PLANE_PITCH * 2) + (size_t)jc * 16;
-                    cp_async16(dst, src);
-                    cp_async16(dst + TILE_BYTES, src + D * 2);
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const int r = 4 * k4 + rq;
+                        const int ri = __shfl_sync(0xffffffffu, idx0[ks], r);
+                        const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((jc ^ (r & 7)) << 4);
+                        const char *src = reinterpret_cast<const char *>(S_pl) + (size_t)ri * (PLANE_PITCH * 2) + (size_t)jc * 16;
+                        cp_async16(dst, src);
+                        cp_async16(dst + TILE_BYTES, src + D * 2);
+                    }
                 }
-                cp_async_arrive_noinc(bar_full(slot));
+                cp_async_arrive_noinc(bar_full(slot));             // fires when all of this lane's copies have landed
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_full(slot));
+                if (lane == 0) mbar_arrive(bar_full(slot));        // releases the rating chunks written above
             } else {
-                int r[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) r[i] = __shfl_sync(0xffffffffu, idx0, i);
-                mbar_wait(bar_empty(slot), ((c / NSTG_) & 1) ^ 1);
-                if (lane < 16) {
-                    __half rh, rl;
-                    split_half(rt0, rh, rl);
-                    const uint32_t off = (uint32_t)lane * 128u + (((uint32_t)lane & 7u) << 4);
-                    const uint32_t w0 = (uint32_t)__half_as_ushort(rh) | ((uint32_t)__half_as_ushort(rl) << 16);
-                    const uint32_t w1 = (uint32_t)__half_as_ushort(rh) << 16;
-                    *reinterpret_cast<uint32_t *>(sm + SM::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + off) = w0;
-                    *reinterpret_cast<uint32_t *>(sm + SM::ring + slot * STAGE_BYTES + 2 * TILE_BYTES + (off ^ 16u)) = w1;
-                }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_expect_tx(bar_full(slot), 2 * TILE_BYTES);
+                if (lane == 0) mbar_expect_tx(bar_full(slot), (dbg & 4) ? 0u : KS * 2 * TILE_BYTES);
                 __syncwarp();
+                if (!(dbg & 4)) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    tma_gather4_pair(stage + t * 512, stage + TILE_BYTES + t * 512, &map_pl, bar_full(slot), r[4 * t], r[4 * t + 1],
-                                     r[4 * t + 2], r[4 * t + 3]);
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const uint32_t stage = stage0 + ks * STAGE_BYTES;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int r0 = __shfl_sync(0xffffffffu, idx0[ks], 4 * t), r1 = __shfl_sync(0xffffffffu, idx0[ks], 4 * t + 1);
+                            const int r2 = __shfl_sync(0xffffffffu, idx0[ks], 4 * t + 2), r3 = __shfl_sync(0xffffffffu, idx0[ks], 4 * t + 3);
+                            tma_gather4_pair(stage + t * 512, stage + TILE_BYTES + t * 512, &map_pl, bar_full(slot), r0, r1, r2, r3);
+                        }
+                    }
+                }
             }
-            idx0 = idx1; rt0 = rt1;
-            idx1 = idx2; rt1 = rt2;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) { idx0[ks] = idx1[ks]; rt0[ks] = rt1[ks]; }
         }
       } else {
-        // ================================================================== MMA issuer (unchanged from v1)
+        // ================================================================== MMA issuer: one handshake per ring slot, KS x 2 MMAs
         uint32_t job = 0;
         const uint32_t idesc1 = make_idesc(MMA_N1), idesc2 = make_idesc(MMA_N2);
         constexpr uint32_t LBO_T = (uint32_t)(TILE_BYTES >> 4) << 16, LBO_B2 = (uint32_t)((2 * TILE_BYTES + 16) >> 4) << 16;
@@ -883,12 +933,17 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64_v2(
             for (int st = 0; st < nst; ++st) {
                 if (!ready) mbar_wait(bar0 + 8u * slot, ph);
                 tc_fence_after();
-                if (LDGSTS) fence_proxy_async();
-                uint32_t nslot = slot + 1, nph = ph, nenc = enc + (STAGE_BYTES >> 4);
+                if (LDGSTS) fence_proxy_async();                   // generic-proxy writes (cp.async, st.shared) -> tensor-core reads
+                uint32_t nslot = slot + 1, nph = ph, nenc = enc + (STG >> 4);
                 if (nslot == NSTG_) { nslot = 0; nph ^= 1u; nenc = enc0; }
-                const uint32_t nready = mbar_test(bar0 + 8u * nslot, nph);
-                tc_stage_mma(d, enc | LBO_T, (enc + (TILE_BYTES >> 4)) | LBO_T, enc | LBO_B2, idesc1, idesc2, st > 0 ? 1u : 0u,
-                             bar0 + 8u * (NSTG_ + slot), bar_acc_full(acc), st == nst - 1 ? 1u : 0u);
+                const uint32_t nready = (dbg & 2) ? 0u : mbar_test(bar0 + 8u * nslot, nph);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint32_t e = enc + ks * (STAGE_BYTES >> 4);
+                    tc_stage_mma2(d, e | LBO_T, (e + (TILE_BYTES >> 4)) | LBO_T, e | LBO_B2, idesc1, idesc2, (st > 0 || ks > 0) ? 1u : 0u,
+                                  bar0 + 8u * (NSTG_ + slot), bar_acc_full(acc), ks == KS - 1 ? 1u : 0u, (ks == KS - 1 && st == nst - 1) ? 1u : 0u,
+                                  (dbg & 8) ? 0u : ((dbg & 1) ? 1u : 2u));
+                }
                 slot = nslot; ph = nph; enc = nenc; ready = nready;
             }
             nst = nst_next;
@@ -966,8 +1021,8 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64_v2(
                     o[D * D + lane] = -bz[lane]; o[D * D + lane + 32] = -bz[lane + 32];
                     __syncwarp();
                 }
-                float x[2];
-                cm::solve_tiles<4>(S, bz, invd, xs, lane, x);
+                float x[2] = {0.f, 0.f};
+                if (!(dbg & 16)) cm::solve_tiles<4>(S, bz, invd, xs, lane, x);
                 const float b0 = x[0], b1 = x[1];
                 __half h0, l0, h1, l1;
                 split_half(b0, h0, l0);
@@ -1013,20 +1068,20 @@ __global__ void k_split_planes(const float *__restrict__ f, int64_t n, __half *_
 }
 
 // ---- stage CSR build (one-off per load / shard geometry)
-__global__ void k_stage_counts(const int64_t *__restrict__ ptr, int64_t n_rows, int32_t *__restrict__ cnt) {
+__global__ void k_stage_counts(const int64_t *__restrict__ ptr, int64_t n_rows, int32_t *__restrict__ cnt, int krows) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r > n_rows) return;
-    cnt[r] = r < n_rows ? (int32_t)((ptr[r + 1] - ptr[r] + KROWS - 1) / KROWS) : 0;
+    cnt[r] = r < n_rows ? (int32_t)((ptr[r + 1] - ptr[r] + krows - 1) / krows) : 0;
 }
 __global__ void k_fill_stages(const int64_t *__restrict__ ptr, const int32_t *__restrict__ col, const float *__restrict__ val,
                               const int32_t *__restrict__ stage_ptr, int64_t n_rows, int zero_row, int32_t *__restrict__ colp,
-                              float *__restrict__ valp) {
+                              float *__restrict__ valp, int krows) {
     const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
     const int64_t s = ptr[row], e = ptr[row + 1];
-    const int64_t base = (int64_t)stage_ptr[row] * KROWS;
-    const int64_t n_pad = (int64_t)(stage_ptr[row + 1] - stage_ptr[row]) * KROWS;
+    const int64_t base = (int64_t)stage_ptr[row] * krows;
+    const int64_t n_pad = (int64_t)(stage_ptr[row + 1] - stage_ptr[row]) * krows;
     for (int64_t t = lane; t < n_pad; t += 32) {
         const int64_t k = s + t;
         colp[base + t] = k < e ? col[k] : zero_row;
@@ -1070,7 +1125,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 int als_tc_supported(const fms_ctx *ctx, int rank) {
-    constexpr size_t need = (size_t)(tc::Smem2<26, 6>::total > tc::Smem::total ? tc::Smem2<26, 6>::total : tc::Smem::total) + 1024;
+    constexpr size_t need = (size_t)(tc::Smem2<6, 6, 4>::total > tc::Smem::total ? tc::Smem2<6, 6, 4>::total : tc::Smem::total) + 1024;
     return rank == tc::D && ctx->smem_optin >= need && get_encode_fn() != nullptr;
 }
 
@@ -1114,17 +1169,17 @@ static int make_map(fms_ctx *ctx, CUtensorMap *m, void *base, int64_t rows) {
     return FMS_OK;
 }
 
-static int ensure_stage_csr(fms_ctx *ctx, int which, int64_t rb, int64_t re, int zero_row, int grid) {
+static int ensure_stage_csr(fms_ctx *ctx, int which, int64_t rb, int64_t re, int zero_row, int grid, int krows) {
     AlsState &A = ctx->als;
     const int64_t n = which == 0 ? A.n_users : A.n_items;
     cudaStream_t st = ctx->stream;
-    const bool refill = A.stage_zero_row[which] != zero_row || A.stage_rb[which] < 0;
+    const bool refill = A.stage_zero_row[which] != zero_row || A.stage_rb[which] < 0 || A.stage_krows[which] != krows;
     if (refill) {
         DevBuf<int32_t> cnt;
         DevBuf<unsigned char> temp;
         FMS_CUDA(ctx, cnt.alloc((size_t)n + 1));
         FMS_CUDA(ctx, A.stage_ptr[which].alloc((size_t)n + 1));
-        tc::k_stage_counts<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(A.ptr[which].p, n, cnt.p);
+        tc::k_stage_counts<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(A.ptr[which].p, n, cnt.p, krows);
         FMS_LAUNCH_CHECK(ctx);
         size_t tb = 0;
         FMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, A.stage_ptr[which].p, n + 1, st));
@@ -1135,15 +1190,16 @@ static int ensure_stage_csr(fms_ctx *ctx, int which, int64_t rb, int64_t re, int
         FMS_CUDA(ctx, cudaMemcpyAsync(&total, A.stage_ptr[which].p + n, sizeof total, cudaMemcpyDeviceToHost, st));
         FMS_CUDA(ctx, cudaStreamSynchronize(st));
         A.total_stages[which] = total;
-        FMS_CUDA(ctx, A.colp[which].alloc((size_t)total * tc::KROWS));
-        FMS_CUDA(ctx, A.valp[which].alloc((size_t)total * tc::KROWS));
+        FMS_CUDA(ctx, A.colp[which].alloc((size_t)total * krows));
+        FMS_CUDA(ctx, A.valp[which].alloc((size_t)total * krows));
         if (n > 0) {
             tc::k_fill_stages<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(A.ptr[which].p, A.col[which].p, A.val[which].p,
                                                                               A.stage_ptr[which].p, n, zero_row, A.colp[which].p,
-                                                                              A.valp[which].p);
+                                                                              A.valp[which].p, krows);
             FMS_LAUNCH_CHECK(ctx);
         }
         A.stage_zero_row[which] = zero_row;
+        A.stage_krows[which] = krows;
         A.stage_rb[which] = -2;                                    // force the partition below
     }
     if (A.stage_rb[which] != rb || A.stage_re[which] != re || A.stage_grid[which] != grid) {
@@ -1171,13 +1227,15 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
     const int n_peers = A.peer_n[which];
     const int64_t rows = re - rb;
     const int grid = (int)(rows < ctx->sm_count ? rows : ctx->sm_count);
-    FMS_TRY(ensure_stage_csr(ctx, which, rb, re, zero_row, grid));
     // producer flavour: LDGSTS for short rows (see the kernel), TMA gather4 for long ones
     const int64_t n_side = which == 0 ? A.n_users : A.n_items;
     const bool short_rows = n_side > 0 && A.nnz / n_side < 16 * tc::KROWS;
-    const bool ldgsts = !dump && (A.kernel == FMS_ALS_KERNEL_TC_LDGSTS || (A.kernel != FMS_ALS_KERNEL_TC_TMA && short_rows));
+    static const int force_kernel = getenv("FMS_ALS_KERNEL") ? atoi(getenv("FMS_ALS_KERNEL")) : 0;     // experiments: 3 = TMA, 4 = LDGSTS producers
+    const int kern = force_kernel ? force_kernel : A.kernel;
+    const bool ldgsts = !dump && (kern == FMS_ALS_KERNEL_TC_LDGSTS || (kern != FMS_ALS_KERNEL_TC_TMA && short_rows));
     static const bool use_v1 = getenv("FMS_ALS_TC_V1") != nullptr;             // A/B switch: the round-1 kernel (CUDA-core solver)
     if (use_v1) {
+        FMS_TRY(ensure_stage_csr(ctx, which, rb, re, zero_row, grid, tc::KROWS));
         const size_t smem = (size_t)tc::Smem::total + 1024;
 #define FMS_TC_LAUNCH(DUMPF, LDG, DUMP_PTR)                                                                                          \
     do {                                                                                                                             \
@@ -1191,21 +1249,27 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
         else FMS_TC_LAUNCH(false, false, nullptr);
 #undef FMS_TC_LAUNCH
     } else {
-        // v2: ring depth / active solver warps per row-length regime (many short systems: 12 solver warps, 13 stages;
-        // few long ones: 6 solver warps, 26 stages of gathers in flight)
-#define FMS_TC2_LAUNCH(DUMPF, LDG, NS, NA, DUMP_PTR)                                                                                    \
+        // v2: ring slots of KS x 16 ratings (one producer / issuer handshake per slot), ring depth and active solver warps per
+        // row-length regime: many short systems -> 2 x 16 ratings per slot, 7 slots (84 KB), 12 solver warps; few long ones ->
+        // 4 x 16 ratings per slot, 6 slots (144 KB of gathers in flight, 6 of the 7 producer warps active), 6 solver warps
+        static const int dbg = getenv("FMS_TC_DBG") ? atoi(getenv("FMS_TC_DBG")) : 0;   // timing experiments (wrong results): see the kernel
+        const int ks = short_rows ? 2 : 4;
+        FMS_TRY(ensure_stage_csr(ctx, which, rb, re, zero_row, grid, tc::KROWS * ks));
+#define FMS_TC2_LAUNCH(DUMPF, LDG, NS, NA, KSV, DUMP_PTR)                                                                               \
     do {                                                                                                                             \
-        const size_t smem = (size_t)tc::Smem2<NS, NA>::total + 1024;                                                                  \
-        FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64_v2<DUMPF, LDG, NS, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        tc::k_als_rows_tc64_v2<DUMPF, LDG, NS, NA><<<grid, tc::V2_WARPS * 32, smem, ctx->stream>>>(                                    \
+        constexpr int NPV = NS < tc::N_PROD ? NS : tc::N_PROD;                                                                        \
+        const size_t smem = (size_t)tc::Smem2<NS, NA, KSV>::total + 1024;                                                             \
+        FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64_v2<DUMPF, LDG, NS, NA, KSV, NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        tc::k_als_rows_tc64_v2<DUMPF, LDG, NS, NA, KSV, NPV><<<grid, tc::V2_WARPS * 32, smem, ctx->stream>>>(                          \
             m_pl, A.ptr[which].p, A.stage_ptr[which].p, A.colp[which].p, A.valp[which].p, A.cta_rows[which].p, A.fac[which].p, t_hi,  \
-            lambda, rb, A.info.p, DUMP_PTR, peers, n_peers, p_hi);                                                                   \
+            lambda, rb, A.info.p, DUMP_PTR, peers, n_peers, p_hi, dbg);                                                              \
     } while (0)
-        if (dump) FMS_TC2_LAUNCH(true, false, 13, 12, dump);
-        else if (short_rows && ldgsts) FMS_TC2_LAUNCH(false, true, 13, 12, nullptr);
-        else if (short_rows) FMS_TC2_LAUNCH(false, false, 13, 12, nullptr);
-        else if (ldgsts) FMS_TC2_LAUNCH(false, true, 26, 6, nullptr);
-        else FMS_TC2_LAUNCH(false, false, 26, 6, nullptr);
+        if (dump && short_rows) FMS_TC2_LAUNCH(true, false, 7, 12, 2, dump);
+        else if (dump) FMS_TC2_LAUNCH(true, false, 6, 6, 4, dump);
+        else if (short_rows && ldgsts) FMS_TC2_LAUNCH(false, true, 7, 12, 2, nullptr);
+        else if (short_rows) FMS_TC2_LAUNCH(false, false, 7, 12, 2, nullptr);
+        else if (ldgsts) FMS_TC2_LAUNCH(false, true, 6, 6, 4, nullptr);
+        else FMS_TC2_LAUNCH(false, false, 6, 6, 4, nullptr);
 #undef FMS_TC2_LAUNCH
     }
     FMS_LAUNCH_CHECK(ctx);
@@ -1274,6 +1338,21 @@ int als_tc_open_peers(fms_ctx *ctx, int s, const void *handles, int n) {
     FMS_CUDA(ctx, A.peer_tab[s].alloc(64));
     FMS_CUDA(ctx, cudaMemcpyAsync(A.peer_tab[s].p, tab, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, ctx->stream));
     FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
+// replicas inside ONE process (group ctx): the peers' plane buffers are ordinary device pointers (peer access enabled)
+int als_tc_set_peers_direct(fms_ctx *ctx, int s, void *const *ptrs, int n) {
+    AlsState &A = ctx->als;
+    if (n != A.shard_count || n > 64) return fail(ctx, FMS_ERR_INVALID_ARG, "peer table: %d pointers for %d shards", n, A.shard_count);
+    FMS_TRY(ensure_planes(ctx, s));
+    als_tc_close_peers(ctx, s);
+    unsigned long long tab[64];
+    for (int r = 0; r < n; ++r) tab[r] = (unsigned long long)(uintptr_t)(r == A.shard_index ? (void *)A.plane[s].p : ptrs[r]);
+    FMS_CUDA(ctx, A.peer_tab[s].alloc(64));
+    FMS_CUDA(ctx, cudaMemcpyAsync(A.peer_tab[s].p, tab, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    A.peer_n[s] = n;
     return FMS_OK;
 }
 

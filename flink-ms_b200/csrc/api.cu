@@ -23,9 +23,9 @@ FMS_API int fms_version(void) { return 100; }
 FMS_API int fms_create(fms_ctx **out, const int *device_ids, int n_devices) {
     if (!out) return FMS_ERR_INVALID_ARG;
     *out = nullptr;
-    if (n_devices != 1) {
-        g_create_error = "fms_create: n_devices must be 1 (one process per GPU; shard with one ctx per rank)";
-        return FMS_ERR_UNSUPPORTED;
+    if (n_devices < 1 || n_devices > 64 || (n_devices > 1 && !device_ids)) {
+        g_create_error = "fms_create: n_devices must be in 1 .. 64 (and device_ids given when it is > 1)";
+        return FMS_ERR_INVALID_ARG;
     }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -33,6 +33,21 @@ FMS_API int fms_create(fms_ctx **out, const int *device_ids, int n_devices) {
         g_create_error = std::string("fms_create: no CUDA device (") + cudaGetErrorString(e) + ") -- libflinkms_b200 has no CPU fallback";
         cudaGetLastError();
         return FMS_ERR_CUDA;
+    }
+    if (n_devices > 1) {
+        // a GROUP: one single-GPU member per device, sequenced by the parent (csrc/group.cu)
+        fms_ctx *P = new (std::nothrow) fms_ctx();
+        if (!P) return FMS_ERR_OOM;
+        P->device = device_ids[0];
+        const int rc = group_create(P, device_ids, n_devices);
+        if (rc != FMS_OK) {
+            g_create_error = P->err;
+            group_destroy(P);
+            delete P;
+            return rc;
+        }
+        *out = P;
+        return FMS_OK;
     }
     int dev = 0;
     if (device_ids) dev = device_ids[0];
@@ -71,6 +86,7 @@ FMS_API int fms_create(fms_ctx **out, const int *device_ids, int n_devices) {
 
 FMS_API void fms_destroy(fms_ctx *ctx) {
     if (!ctx) return;
+    if (!ctx->members.empty()) { group_destroy(ctx); delete ctx; return; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     als_tc_close_peers(ctx, 0);
@@ -82,9 +98,38 @@ FMS_API void fms_destroy(fms_ctx *ctx) {
 }
 
 FMS_API const char *fms_last_error(const fms_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
-FMS_API void *fms_stream(fms_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
-FMS_API int64_t fms_launch_count(const fms_ctx *ctx) { return ctx ? ctx->launches : 0; }
+// group ctx: entry points that work on the fitted model are served by member 0 (every member holds the full model after a fit)
+#define GROUP_FORWARD(ctx, call)                                         \
+    do {                                                                 \
+        if ((ctx) && !(ctx)->members.empty()) {                          \
+            fms_ctx *m0 = (ctx)->members[0];                             \
+            cudaSetDevice(m0->device);                                   \
+            const int rc_ = (call);                                      \
+            if (rc_ != FMS_OK) (ctx)->err = m0->err;                     \
+            return rc_;                                                  \
+        }                                                                \
+    } while (0)
+#define GROUP_UNSUPPORTED(ctx, name)                                     \
+    do {                                                                 \
+        if ((ctx) && !(ctx)->members.empty())                            \
+            return fail((ctx), FMS_ERR_UNSUPPORTED, name ": step-level entry points need a single-device ctx (a group ctx runs whole fits)"); \
+    } while (0)
+
+FMS_API void *fms_stream(fms_ctx *ctx) { return !ctx ? nullptr : (ctx->members.empty() ? (void *)ctx->stream : (void *)ctx->members[0]->stream); }
+FMS_API int64_t fms_launch_count(const fms_ctx *ctx) {
+    if (!ctx) return 0;
+    int64_t n = ctx->launches;
+    for (const fms_ctx *m : ctx->members) n += m->launches;
+    return n;
+}
 FMS_API int fms_synchronize(fms_ctx *ctx) {
+    if (ctx && !ctx->members.empty()) {
+        for (fms_ctx *m : ctx->members) {
+            const int rc = fms_synchronize(m);
+            if (rc != FMS_OK) { ctx->err = m->err; return rc; }
+        }
+        return FMS_OK;
+    }
     CHECK_CTX(ctx);
     FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FMS_OK;
@@ -93,15 +138,17 @@ FMS_API int fms_synchronize(fms_ctx *ctx) {
 // ====================================================================================================== ALS
 FMS_API int fms_als_load(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t nnz,
                          int shard_index, int shard_count, int64_t *n_users, int64_t *n_items) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_load");
     CHECK_CTX(ctx);
     if (nnz < 0 || (nnz > 0 && (!user || !item || !rating))) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_load: null input or nnz < 0");
     if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count)
         return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_load: bad shard %d/%d", shard_index, shard_count);
     if (nnz >= ((int64_t)1 << 31) * 8) return fail(ctx, FMS_ERR_UNSUPPORTED, "fms_als_load: nnz too large");
+    NvtxRange nvtx_("fms.als.load (H2D + createBlockInformation)");
     AlsState &A = ctx->als;
     A.loaded = A.inited = false;
     A.model_external = false;
-    FMS_TRY(als_build_csr(ctx, user, item, rating, nnz));
+    FMS_TRY(als_build_csr(ctx, user, item, rating, nnz, shard_index, shard_count));
     A.stage_rb[0] = A.stage_rb[1] = -1;                // stage layout of the tensor-core path is rebuilt lazily
     A.stage_zero_row[0] = A.stage_zero_row[1] = -1;
     A.shard_index = shard_index;
@@ -115,6 +162,7 @@ FMS_API int fms_als_load(fms_ctx *ctx, const int64_t *user, const int64_t *item,
 }
 
 FMS_API int fms_als_init(fms_ctx *ctx, int rank, int64_t seed) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_init");
     CHECK_CTX(ctx);
     AlsState &A = ctx->als;
     if (!A.loaded) return fail(ctx, FMS_ERR_STATE, "fms_als_init: no ratings loaded");
@@ -127,6 +175,7 @@ FMS_API int fms_als_init(fms_ctx *ctx, int rank, int64_t seed) {
 }
 
 FMS_API int fms_als_set_kernel(fms_ctx *ctx, int kernel) {
+    if (ctx) for (fms_ctx *m : ctx->members) { const int rc_ = fms_als_set_kernel(m, kernel); if (rc_ != FMS_OK) { ctx->err = m->err; return rc_; } }
     if (!ctx) return FMS_ERR_INVALID_ARG;
     if (kernel < FMS_ALS_KERNEL_AUTO || kernel > FMS_ALS_KERNEL_TC_LDGSTS) return fail(ctx, FMS_ERR_INVALID_ARG, "bad ALS kernel id %d", kernel);
     ctx->als.kernel = kernel;
@@ -144,6 +193,7 @@ static int als_half_step_rows(fms_ctx *ctx, int which, double lambda, int chunk,
     const int64_t sb = S * A.shard_index;
     const int64_t rb = std::min<int64_t>(n, sb + std::min<int64_t>(S, c * chunk));
     const int64_t re = std::min<int64_t>(n, sb + std::min<int64_t>(S, c * (chunk + 1)));
+    NvtxRange nvtx_(which == FMS_USERS ? "fms.als.half_step users" : "fms.als.half_step items");
     if (chunk == 0) FMS_CUDA(ctx, cudaMemsetAsync(A.info.p, 0, sizeof(int), ctx->stream));
     bool tc = false;
     if (A.kernel != FMS_ALS_KERNEL_GENERIC) tc = als_tc_supported(ctx, A.rank) != 0;
@@ -157,16 +207,19 @@ static int als_half_step_rows(fms_ctx *ctx, int which, double lambda, int chunk,
 }
 
 FMS_API int fms_als_half_step(fms_ctx *ctx, int which, double lambda) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_half_step");
     CHECK_CTX(ctx);
     return als_half_step_rows(ctx, which, lambda, 0, 1, "fms_als_half_step");
 }
 
 FMS_API int fms_als_half_step_chunk(fms_ctx *ctx, int which, double lambda, int chunk, int n_chunks) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_half_step_chunk");
     CHECK_CTX(ctx);
     return als_half_step_rows(ctx, which, lambda, chunk, n_chunks, "fms_als_half_step_chunk");
 }
 
 FMS_API int fms_als_last_info(fms_ctx *ctx, int64_t *bad_rows) {
+    GROUP_FORWARD(ctx, fms_als_last_info(m0, bad_rows));
     CHECK_CTX(ctx);
     AlsState &A = ctx->als;
     if (!A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_last_info: no half-step run");
@@ -179,6 +232,7 @@ FMS_API int fms_als_last_info(fms_ctx *ctx, int64_t *bad_rows) {
 
 FMS_API int fms_als_factors_device(fms_ctx *ctx, int which, void **dev_ptr, int64_t *rows_padded, int64_t *shard_begin,
                                    int64_t *shard_end) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_factors_device");
     if (!ctx) return FMS_ERR_INVALID_ARG;
     AlsState &A = ctx->als;
     if (!A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_factors_device: init first");
@@ -192,6 +246,7 @@ FMS_API int fms_als_factors_device(fms_ctx *ctx, int which, void **dev_ptr, int6
 }
 
 FMS_API int fms_als_factors_updated(fms_ctx *ctx, int which) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_factors_updated");
     if (!ctx) return FMS_ERR_INVALID_ARG;
     if (which != 0 && which != 1) return fail(ctx, FMS_ERR_INVALID_ARG, "which = %d", which);
     ctx->als.fac64_valid = false;
@@ -200,6 +255,7 @@ FMS_API int fms_als_factors_updated(fms_ctx *ctx, int which) {
 }
 
 FMS_API int fms_als_planes_device(fms_ctx *ctx, int which, void **hi, void **lo, int64_t *rows_padded) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_planes_device");
     CHECK_CTX(ctx);
     AlsState &A = ctx->als;
     if (!A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_planes_device: init first");
@@ -209,6 +265,7 @@ FMS_API int fms_als_planes_device(fms_ctx *ctx, int which, void **hi, void **lo,
 }
 
 FMS_API int fms_als_planes_ipc_handle(fms_ctx *ctx, int which, void *handle64) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_planes_ipc_handle");
     CHECK_CTX(ctx);
     AlsState &A = ctx->als;
     if (!A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_planes_ipc_handle: init first");
@@ -218,6 +275,7 @@ FMS_API int fms_als_planes_ipc_handle(fms_ctx *ctx, int which, void *handle64) {
 }
 
 FMS_API int fms_als_planes_open_peers(fms_ctx *ctx, int which, const void *handles, int n) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_planes_open_peers");
     CHECK_CTX(ctx);
     AlsState &A = ctx->als;
     if (!A.inited) return fail(ctx, FMS_ERR_STATE, "fms_als_planes_open_peers: init first");
@@ -229,6 +287,7 @@ FMS_API int fms_als_planes_open_peers(fms_ctx *ctx, int which, const void *handl
 }
 
 FMS_API int fms_als_planes_peer_count(fms_ctx *ctx, int which, int *n_peers) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_planes_peer_count");
     if (!ctx) return FMS_ERR_INVALID_ARG;
     if ((which != 0 && which != 1) || !n_peers) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_planes_peer_count: bad arguments");
     *n_peers = ctx->als.peer_n[which];
@@ -236,6 +295,7 @@ FMS_API int fms_als_planes_peer_count(fms_ctx *ctx, int which, int *n_peers) {
 }
 
 FMS_API int fms_als_planes_updated(fms_ctx *ctx, int which) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_planes_updated");
     if (!ctx) return FMS_ERR_INVALID_ARG;
     if (which != 0 && which != 1) return fail(ctx, FMS_ERR_INVALID_ARG, "which = %d", which);
     ctx->als.plane_valid[which] = true;      // every shard of the planes is current; the fp32 matrix may still be stale
@@ -244,15 +304,37 @@ FMS_API int fms_als_planes_updated(fms_ctx *ctx, int which) {
 
 FMS_API int fms_als_fit(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t nnz, int rank,
                         int iterations, double lambda, int64_t seed, int64_t *n_users, int64_t *n_items) {
+    if (ctx && !ctx->members.empty()) {
+        if (iterations < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_fit: iterations %d < 0", iterations);
+        if (rank < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_fit: rank %d < 1", rank);
+        return group_als_fit(ctx, user, item, rating, nnz, rank, iterations, lambda, seed, n_users, n_items);
+    }
     CHECK_CTX(ctx);
     if (iterations < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_fit: iterations %d < 0", iterations);
     if (rank < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_fit: rank %d < 1", rank);
+    NvtxRange nvtx_("fms.als.fit");
+    // FMS_LOG_JSON=1: one JSON line per iteration on stderr (costs a stream synchronisation per iteration, off by default)
+    static const bool log_json = getenv("FMS_LOG_JSON") != nullptr;
     FMS_TRY(fms_als_load(ctx, user, item, rating, nnz, 0, 1, n_users, n_items));
     FMS_TRY(fms_als_init(ctx, rank, seed));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (log_json) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
     for (int t = 0; t < iterations; ++t) {
+        if (log_json) cudaEventRecord(e0, ctx->stream);
         FMS_TRY(fms_als_half_step(ctx, FMS_USERS, lambda));
         FMS_TRY(fms_als_half_step(ctx, FMS_ITEMS, lambda));
+        if (log_json) {
+            cudaEventRecord(e1, ctx->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            int64_t bad = 0;
+            fms_als_last_info(ctx, &bad);
+            fprintf(stderr, "{\"event\": \"als_iteration\", \"iteration\": %d, \"ms\": %.4f, \"ratings_per_s\": %.4g, \"rank\": %d, \"bad_rows\": %lld}\n", t, ms,
+                    ms > 0 ? (double)nnz / (ms * 1e-3) : 0.0, rank, (long long)bad);
+        }
     }
+    if (log_json) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
     FMS_TRY(fms_als_half_step(ctx, FMS_USERS, lambda));   // the extra user half-step after the loop
     // dposv's info: FlinkML ignores it and so does the fit, but a model with broken-down rows (NaN factors: a system that
     // is not positive definite, or |rating| / |factor| beyond what the kernel's operand format holds) must not leave
@@ -266,6 +348,7 @@ FMS_API int fms_als_fit(fms_ctx *ctx, const int64_t *user, const int64_t *item, 
 }
 
 FMS_API int fms_als_get_factors(fms_ctx *ctx, int which, int64_t *ids, double *factors) {
+    GROUP_FORWARD(ctx, fms_als_get_factors(m0, which, ids, factors));
     CHECK_CTX(ctx);
     AlsState &A = ctx->als;
     if (!A.inited && !A.model_external) return fail(ctx, FMS_ERR_STATE, "The ALS model has not been fitted.");
@@ -281,6 +364,7 @@ FMS_API int fms_als_get_factors(fms_ctx *ctx, int which, int64_t *ids, double *f
 }
 
 FMS_API int fms_als_get_factor_rows(fms_ctx *ctx, int which, int64_t row_begin, int64_t row_end, int64_t *ids, double *factors) {
+    GROUP_FORWARD(ctx, fms_als_get_factor_rows(m0, which, row_begin, row_end, ids, factors));
     CHECK_CTX(ctx);
     AlsState &A = ctx->als;
     if (!A.inited && !A.model_external) return fail(ctx, FMS_ERR_STATE, "The ALS model has not been fitted.");
@@ -299,6 +383,7 @@ FMS_API int fms_als_get_factor_rows(fms_ctx *ctx, int which, int64_t row_begin, 
 
 FMS_API int fms_als_set_model(fms_ctx *ctx, const int64_t *user_ids, const double *user_factors, int64_t n_users,
                               const int64_t *item_ids, const double *item_factors, int64_t n_items, int rank) {
+    GROUP_FORWARD(ctx, fms_als_set_model(m0, user_ids, user_factors, n_users, item_ids, item_factors, n_items, rank));
     CHECK_CTX(ctx);
     if (n_users < 0 || n_items < 0 || rank < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_set_model: bad sizes");
     if ((n_users && (!user_ids || !user_factors)) || (n_items && (!item_ids || !item_factors)))
@@ -355,6 +440,7 @@ static int predict_common(fms_ctx *ctx, const int64_t *u, const int64_t *i, int6
 }
 
 FMS_API int fms_als_predict(fms_ctx *ctx, const int64_t *u, const int64_t *i, int64_t n, double *out, uint8_t *found) {
+    GROUP_FORWARD(ctx, fms_als_predict(m0, u, i, n, out, found));
     CHECK_CTX(ctx);
     if (n && !out) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_predict: out is null");
     DevBuf<int64_t> &du = ctx->als.q_u, &di = ctx->als.q_i;
@@ -371,6 +457,7 @@ FMS_API int fms_als_predict(fms_ctx *ctx, const int64_t *u, const int64_t *i, in
 
 FMS_API int fms_als_mse(fms_ctx *ctx, const int64_t *u, const int64_t *i, const double *rating, int64_t n, double *mse,
                         int64_t *n_used) {
+    GROUP_FORWARD(ctx, fms_als_mse(m0, u, i, rating, n, mse, n_used));
     CHECK_CTX(ctx);
     if (n && !rating) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_mse: rating is null");
     DevBuf<int64_t> &du = ctx->als.q_u, &di = ctx->als.q_i;
@@ -397,6 +484,7 @@ FMS_API int fms_als_mse(fms_ctx *ctx, const int64_t *u, const int64_t *i, const 
 FMS_API int fms_als_sgd_step(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t n, double learning_rate,
                              double user_reg, double item_reg, const double *user_mean, const double *item_mean, int apply,
                              double *out_user, double *out_item) {
+    GROUP_FORWARD(ctx, fms_als_sgd_step(m0, user, item, rating, n, learning_rate, user_reg, item_reg, user_mean, item_mean, apply, out_user, out_item));
     CHECK_CTX(ctx);
     AlsState &A = ctx->als;
     if (!A.inited && !A.model_external) return fail(ctx, FMS_ERR_STATE, "The ALS model has not been fitted.");
@@ -428,6 +516,7 @@ FMS_API int fms_als_sgd_step(fms_ctx *ctx, const int64_t *user, const int64_t *i
 // ====================================================================================================== N4 ingest
 FMS_API int fms_parse_ratings_csv(fms_ctx *ctx, const char *text, int64_t nbytes, char delimiter, int ignore_first_line, int64_t *user,
                                   int64_t *item, double *rating, int64_t capacity, int64_t *n_rows) {
+    GROUP_FORWARD(ctx, fms_parse_ratings_csv(m0, text, nbytes, delimiter, ignore_first_line, user, item, rating, capacity, n_rows));
     CHECK_CTX(ctx);
     if (nbytes < 0 || (nbytes && !text) || capacity < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_parse_ratings_csv: bad arguments");
     if (delimiter == '\n' || delimiter == '\r') return fail(ctx, FMS_ERR_INVALID_ARG, "fms_parse_ratings_csv: the field delimiter cannot be a line break");
@@ -436,6 +525,7 @@ FMS_API int fms_parse_ratings_csv(fms_ctx *ctx, const char *text, int64_t nbytes
 
 FMS_API int fms_parse_libsvm(fms_ctx *ctx, const char *text, int64_t nbytes, double *label, int64_t row_capacity, int64_t *csr_ptr,
                              int32_t *csr_idx, double *csr_val, int64_t nnz_capacity, int64_t *n_rows, int64_t *nnz, int32_t *dim) {
+    GROUP_FORWARD(ctx, fms_parse_libsvm(m0, text, nbytes, label, row_capacity, csr_ptr, csr_idx, csr_val, nnz_capacity, n_rows, nnz, dim));
     CHECK_CTX(ctx);
     if (nbytes < 0 || (nbytes && !text) || row_capacity < 0 || nnz_capacity < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_parse_libsvm: bad arguments");
     return ingest_libsvm(ctx, text, nbytes, label, row_capacity, csr_ptr, csr_idx, csr_val, nnz_capacity, n_rows, nnz, dim);
@@ -462,6 +552,7 @@ static int upload_f64_as_f32(fms_ctx *ctx, const double *h, int64_t n, float *d_
 }
 
 FMS_API int fms_svm_set_kernel(fms_ctx *ctx, int kernel) {
+    if (ctx) for (fms_ctx *m : ctx->members) { const int rc_ = fms_svm_set_kernel(m, kernel); if (rc_ != FMS_OK) { ctx->err = m->err; return rc_; } }
     if (!ctx) return FMS_ERR_INVALID_ARG;
     if (kernel < FMS_SVM_KERNEL_AUTO || kernel > FMS_SVM_KERNEL_WARP) return fail(ctx, FMS_ERR_INVALID_ARG, "bad SVM kernel id %d", kernel);
     ctx->svm.kernel = kernel;
@@ -471,7 +562,9 @@ FMS_API int fms_svm_set_kernel(fms_ctx *ctx, int kernel) {
 FMS_API int fms_svm_load(fms_ctx *ctx, const void *X, int x_dtype, int X_is_device, const int64_t *csr_ptr, const int32_t *csr_idx,
                          const double *y, int64_t n, int32_t dim, const int32_t *block_id, int blocks, int shard_index,
                          int shard_count, double regularization, double stepsize, int64_t seed, int rng_mode) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_load");
     CHECK_CTX(ctx);
+    NvtxRange nvtx_("fms.svm.load (group rows by block, H2D)");
     SvmState &S = ctx->svm;
     S.loaded = false;
     if (n < 0 || dim < 1 || blocks < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: n=%lld dim=%d blocks=%d", (long long)n, dim, blocks);
@@ -484,7 +577,7 @@ FMS_API int fms_svm_load(fms_ctx *ctx, const void *X, int x_dtype, int X_is_devi
     if (n >= ((int64_t)1 << 31)) return fail(ctx, FMS_ERR_UNSUPPORTED, "fms_svm_load: n >= 2^31 (Random.nextInt bound is an int)");
     if (!(regularization > 0.0)) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_load: regularization must be > 0");
     cudaStream_t st = ctx->stream;
-    S.n = n; S.dim = dim; S.blocks = blocks; S.shard_index = shard_index; S.shard_count = shard_count;
+    S.n = n; S.n_total = n; S.dim = dim; S.blocks = blocks; S.shard_index = shard_index; S.shard_count = shard_count;
     S.lambda = regularization; S.stepsize = stepsize; S.seed = seed; S.rng_mode = rng_mode;
     // ---- group rows by block (arrival order inside a block)
     std::vector<int64_t> cnt((size_t)blocks + 1, 0);
@@ -561,12 +654,14 @@ FMS_API int fms_svm_load(fms_ctx *ctx, const void *X, int x_dtype, int X_is_devi
 }
 
 FMS_API int fms_svm_sweep(fms_ctx *ctx, int64_t local_iterations) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_sweep");
     CHECK_CTX(ctx);
     if (!ctx->svm.loaded) return fail(ctx, FMS_ERR_STATE, "fms_svm_sweep: load first");
     return svm_launch_sweep(ctx, local_iterations);
 }
 
 FMS_API int fms_svm_delta_device(fms_ctx *ctx, void **dev_ptr, int32_t *dim) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_delta_device");
     if (!ctx) return FMS_ERR_INVALID_ARG;
     if (!ctx->svm.loaded) return fail(ctx, FMS_ERR_STATE, "fms_svm_delta_device: load first");
     if (dev_ptr) *dev_ptr = ctx->svm.delta.p;
@@ -575,6 +670,7 @@ FMS_API int fms_svm_delta_device(fms_ctx *ctx, void **dev_ptr, int32_t *dim) {
 }
 
 FMS_API int fms_svm_apply_delta(fms_ctx *ctx) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_apply_delta");
     CHECK_CTX(ctx);
     if (!ctx->svm.loaded) return fail(ctx, FMS_ERR_STATE, "fms_svm_apply_delta: load first");
     return svm_launch_apply(ctx);
@@ -598,6 +694,7 @@ static int svm_ensure_w64(fms_ctx *ctx) {
 }
 
 FMS_API int fms_svm_get_weights(fms_ctx *ctx, double *w, int32_t dim) {
+    GROUP_FORWARD(ctx, fms_svm_get_weights(m0, w, dim));
     CHECK_CTX(ctx);
     SvmState &S = ctx->svm;
     FMS_TRY(svm_ensure_w64(ctx));
@@ -608,6 +705,7 @@ FMS_API int fms_svm_get_weights(fms_ctx *ctx, double *w, int32_t dim) {
 }
 
 FMS_API int fms_svm_set_weights(fms_ctx *ctx, const double *w, int32_t dim) {
+    GROUP_FORWARD(ctx, fms_svm_set_weights(m0, w, dim));
     CHECK_CTX(ctx);
     if (!w || dim < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_set_weights: null or dim < 1");
     SvmState &S = ctx->svm;
@@ -620,6 +718,7 @@ FMS_API int fms_svm_set_weights(fms_ctx *ctx, const double *w, int32_t dim) {
 }
 
 FMS_API int fms_svm_get_alpha(fms_ctx *ctx, double *alpha, int64_t n) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_get_alpha");
     CHECK_CTX(ctx);
     SvmState &S = ctx->svm;
     if (!S.loaded) return fail(ctx, FMS_ERR_STATE, "fms_svm_get_alpha: load first");
@@ -637,11 +736,19 @@ FMS_API int fms_svm_get_alpha(fms_ctx *ctx, double *alpha, int64_t n) {
 FMS_API int fms_svm_fit(fms_ctx *ctx, const void *X, int x_dtype, const int64_t *csr_ptr, const int32_t *csr_idx, const double *y,
                         int64_t n, int32_t dim, const int32_t *block_id, int blocks, int iterations, int64_t local_iterations,
                         double regularization, double stepsize, int64_t seed, int rng_mode, double *w_out) {
+    if (ctx && !ctx->members.empty()) {
+        if (iterations < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_fit: iterations < 0");
+        if (!w_out) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_fit: w_out is null");
+        return group_svm_fit(ctx, X, x_dtype, csr_ptr, csr_idx, y, n, dim, block_id, blocks, iterations, local_iterations, regularization,
+                             stepsize, seed, rng_mode, w_out);
+    }
     CHECK_CTX(ctx);
     if (iterations < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_fit: iterations < 0");
     if (!w_out) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_fit: w_out is null");
     FMS_TRY(fms_svm_load(ctx, X, x_dtype, 0, csr_ptr, csr_idx, y, n, dim, block_id, blocks, 0, 1, regularization, stepsize, seed, rng_mode));
+    NvtxRange nvtx_("fms.svm.fit rounds");
     for (int t = 0; t < iterations; ++t) {
+        NvtxRange nvtx_r("fms.svm.round (sweep + reduce + apply)");
         FMS_TRY(svm_launch_sweep(ctx, local_iterations));
         FMS_TRY(svm_launch_apply(ctx));
     }
@@ -650,6 +757,7 @@ FMS_API int fms_svm_fit(fms_ctx *ctx, const void *X, int x_dtype, const int64_t 
 
 FMS_API int fms_svm_predict(fms_ctx *ctx, const void *X, int x_dtype, const int64_t *csr_ptr, const int32_t *csr_idx, int64_t n,
                             int32_t dim, const double *w, double threshold, int output_decision_function, double *out) {
+    GROUP_FORWARD(ctx, fms_svm_predict(m0, X, x_dtype, csr_ptr, csr_idx, n, dim, w, threshold, output_decision_function, out));
     CHECK_CTX(ctx);
     SvmState &S = ctx->svm;
     if (n < 0 || dim < 1 || (n && (!X || !out))) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_predict: bad arguments");
@@ -702,6 +810,7 @@ __global__ void k_index_stream(long long seed, int block, int bound, long long c
 }
 
 FMS_API int fms_debug_index_stream(fms_ctx *ctx, int64_t seed, int block, int32_t bound, int64_t count, int32_t *out) {
+    GROUP_FORWARD(ctx, fms_debug_index_stream(m0, seed, block, bound, count, out));
     CHECK_CTX(ctx);
     if (bound < 1 || count < 0 || (count && !out)) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_debug_index_stream: bad arguments");
     if (!count) return FMS_OK;
@@ -715,6 +824,7 @@ FMS_API int fms_debug_index_stream(fms_ctx *ctx, int64_t seed, int block, int32_
 }
 
 FMS_API int fms_debug_als_gramian(fms_ctx *ctx, int which, double lambda, int64_t row_begin, int64_t row_end, float *out) {
+    GROUP_UNSUPPORTED(ctx, "fms_debug_als_gramian");
     CHECK_CTX(ctx);
     AlsState &A = ctx->als;
     if (!A.loaded || !A.inited) return fail(ctx, FMS_ERR_STATE, "fms_debug_als_gramian: load + init first");

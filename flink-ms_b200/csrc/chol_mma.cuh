@@ -39,10 +39,23 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) 
     hi = tf32_rna(x);
     lo = tf32_rna(x - __uint_as_float(hi));
 }
-__device__ __forceinline__ void mma_tf32(float4 &c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c.x), "+f"(c.y), "+f"(c.z), "+f"(c.w)
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+// A B fragment travels as ONE 64-bit value (b0 low, b1 high): ptxas then keeps it in the aligned register pair HMMA wants
+// (as two separate 32-bit variables every use cost two MOVs: ~1 000 of the prototype's 7 300 instructions per system).
+typedef unsigned long long BFrag;
+__device__ __forceinline__ BFrag bfrag(uint32_t b0, uint32_t b1) {
+    BFrag r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(b0), "r"(b1));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float4 &c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, BFrag b) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 b0, b1;\n"
+        "mov.b64 {b0, b1}, %8;\n"
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {b0,b1}, {%0,%1,%2,%3};\n"
+        "}\n"
+        : "+f"(c.x), "+f"(c.y), "+f"(c.z), "+f"(c.w)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "l"(b));
 }
 // A operand from an accumulator-layout tile: rows g / g + 8, k slot t = column 2 t, k slot t + 4 = column 2 t + 1
 struct AFrag {
@@ -52,14 +65,15 @@ struct AFrag {
     }
 };
 // c += A B^T with 3xTF32: hi hi + hi lo + lo hi (the small terms first)
-__device__ __forceinline__ void mma3(float4 &c, const AFrag &a, uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-    mma_tf32(c, a.l0, a.l1, a.l2, a.l3, bh0, bh1);
-    mma_tf32(c, a.h0, a.h1, a.h2, a.h3, bl0, bl1);
-    mma_tf32(c, a.h0, a.h1, a.h2, a.h3, bh0, bh1);
+__device__ __forceinline__ void mma3(float4 &c, const AFrag &a, BFrag bh, BFrag bl) {
+    mma_tf32(c, a.l0, a.l1, a.l2, a.l3, bh);
+    mma_tf32(c, a.h0, a.h1, a.h2, a.h3, bl);
+    mma_tf32(c, a.h0, a.h1, a.h2, a.h3, bh);
 }
 
 __device__ __forceinline__ float rsqrt_nr(float x) {
-    const float r = rsqrtf(x);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));      // bare MUFU.RSQ (rsqrtf() adds a denormal range fix-up)
     return r * fmaf(-0.5f * x * r, r, 1.5f);              // one Newton step: ~1 ulp; a non-positive pivot becomes NaN
 }
 __device__ __forceinline__ float sel4(int t, float a, float b, float c, float d) {
@@ -90,15 +104,15 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
     constexpr int D = TL::D, NT = TL::NT;
     const int g = lane >> 2, t = lane & 3;
     float4 *S4 = reinterpret_cast<float4 *>(S);
-    uint32_t bh0[NT], bh1[NT], bl0[NT], bl1[NT];            // B fragments (hi / lo) of the current panel's L, per n-tile
+    BFrag bh[NT], bl[NT];                                   // B fragments (hi / lo) of the current panel's L, per n-tile
 #pragma unroll
-    for (int j = 0; j < NT; ++j) bh0[j] = bh1[j] = bl0[j] = bl1[j] = 0u;
+    for (int j = 0; j < NT; ++j) bh[j] = bl[j] = 0ull;
 
 #pragma unroll 1
     for (int J = 0; J < NT; ++J) {
         const int Id = J >> 1, h = J & 1;
         // ---- 1. diagonal block, factored redundantly: a[r (r + 1) / 2 + c] = (A + lambda n I)[8 J + r][8 J + c], c <= r
-        uint32_t wb_h0, wb_h1, wb_l0, wb_l1;
+        BFrag wb_h, wb_l;
         {
             const float *Td = S + (Id * (Id + 1) + J) * 128 + 2 * h;
             float a[36];
@@ -135,8 +149,11 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
                 wv[c] = s * rinv[c];
             }
             // B fragment of -W: n = g (row of W), k slot t -> column 2 t, k slot t + 4 -> column 2 t + 1
-            split_tf32(-sel4(t, wv[0], wv[2], wv[4], wv[6]), wb_h0, wb_l0);
-            split_tf32(-sel4(t, wv[1], wv[3], wv[5], wv[7]), wb_h1, wb_l1);
+            uint32_t h0, l0, h1, l1;
+            split_tf32(-sel4(t, wv[0], wv[2], wv[4], wv[6]), h0, l0);
+            split_tf32(-sel4(t, wv[1], wv[3], wv[5], wv[7]), h1, l1);
+            wb_h = bfrag(h0, h1);
+            wb_l = bfrag(l0, l1);
         }
         // ---- 2 + 3. panel tiles: L(I, J) = S(I, J) (-W)^T, then S(I, j) += L(I, J) L(j, J)^T for J < j <= 2 I + 1
 #pragma unroll
@@ -146,7 +163,7 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
                 AFrag af;
                 af.set(sv.x, sv.y, sv.z, sv.w);
                 float4 L = make_float4(0.f, 0.f, 0.f, 0.f);
-                mma3(L, af, wb_h0, wb_h1, wb_l0, wb_l1);
+                mma3(L, af, wb_h, wb_l);
                 if (I == Id) {
                     // rows of the diagonal block: keep the lower triangle (the product reproduces Ld up to rounding noise
                     // above the diagonal); rows of the m-tile above the block belong to finished panels: zero
@@ -156,15 +173,15 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
                 }
                 S4[(I * (I + 1) + J) * 32 + lane] = L;
                 af.set(L.x, L.y, L.z, L.w);
-                bh0[2 * I] = af.h0; bh1[2 * I] = af.h2; bl0[2 * I] = af.l0; bl1[2 * I] = af.l2;                  // rows g     -> n-tile 2 I
-                bh0[2 * I + 1] = af.h1; bh1[2 * I + 1] = af.h3; bl0[2 * I + 1] = af.l1; bl1[2 * I + 1] = af.l3;  // rows g + 8 -> n-tile 2 I + 1
+                bh[2 * I] = bfrag(af.h0, af.h2); bl[2 * I] = bfrag(af.l0, af.l2);                  // rows g     -> n-tile 2 I
+                bh[2 * I + 1] = bfrag(af.h1, af.h3); bl[2 * I + 1] = bfrag(af.l1, af.l3);          // rows g + 8 -> n-tile 2 I + 1
+                // descending j with an early exit: a real (uniform) branch instead of predicated-off HMMA / LDS / STS
 #pragma unroll
-                for (int j = 0; j <= 2 * I + 1; ++j) {
-                    if (j > J) {
-                        float4 c = S4[(I * (I + 1) + j) * 32 + lane];
-                        mma3(c, af, bh0[j], bh1[j], bl0[j], bl1[j]);
-                        S4[(I * (I + 1) + j) * 32 + lane] = c;
-                    }
+                for (int j = 2 * I + 1; j >= 0; --j) {
+                    if (j <= J) break;
+                    float4 c = S4[(I * (I + 1) + j) * 32 + lane];
+                    mma3(c, af, bh[j], bl[j]);
+                    S4[(I * (I + 1) + j) * 32 + lane] = c;
                 }
             }
         }
@@ -177,19 +194,18 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
             split_tf32(bv.x, af.h0, af.l0);
             split_tf32(bv.y, af.h2, af.l2);
             float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            mma3(z, af, wb_h0, wb_h1, wb_l0, wb_l1);
+            mma3(z, af, wb_h, wb_l);
             if (g == 0) *reinterpret_cast<float2 *>(bz + 8 * J + 2 * t) = make_float2(z.x, z.y);
             split_tf32(z.x, af.h0, af.l0);
             split_tf32(z.y, af.h2, af.l2);
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                if (j > J) {
-                    float2 cv = make_float2(0.f, 0.f);
-                    if (g == 0) cv = *reinterpret_cast<const float2 *>(bz + 8 * j + 2 * t);
-                    float4 c = make_float4(cv.x, cv.y, 0.f, 0.f);
-                    mma3(c, af, bh0[j], bh1[j], bl0[j], bl1[j]);
-                    if (g == 0) *reinterpret_cast<float2 *>(bz + 8 * j + 2 * t) = make_float2(c.x, c.y);
-                }
+            for (int j = NT - 1; j >= 0; --j) {
+                if (j <= J) break;
+                float2 cv = make_float2(0.f, 0.f);
+                if (g == 0) cv = *reinterpret_cast<const float2 *>(bz + 8 * j + 2 * t);
+                float4 c = make_float4(cv.x, cv.y, 0.f, 0.f);
+                mma3(c, af, bh[j], bl[j]);
+                if (g == 0) *reinterpret_cast<float2 *>(bz + 8 * j + 2 * t) = make_float2(c.x, c.y);
             }
         }
         __syncwarp();

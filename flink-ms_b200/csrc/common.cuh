@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>            // header-only: ranges are no-ops unless a profiler injects the NVTX library
+
 #include "../../include/flinkms.h"
 
 namespace fms {
@@ -82,12 +84,14 @@ struct AlsState {
     int stage_grid[2] = {0, 0};
     int64_t stage_rb[2] = {-1, -1}, stage_re[2] = {-1, -1};
     int stage_zero_row[2] = {-1, -1};
+    int stage_krows[2] = {0, 0};             // ratings per ring slot the stage layout was padded for (16 x KS)
 };
 
 // --------------------------------------------------------------------------------------------- SVM state
 struct SvmState {
     bool loaded = false;
     int64_t n = 0;
+    int64_t n_total = 0;                     // size of the WHOLE training set (lambda * n of `maximize`); == n unless a group ctx sharded the rows
     int32_t dim = 0;
     int blocks = 0;
     int shard_index = 0, shard_count = 1;
@@ -117,6 +121,7 @@ struct SvmState {
     int32_t w64_dim = 0;
     std::vector<int> local_blocks;           // block ids swept by this rank
     DevBuf<int32_t> d_local_blocks;
+    DevBuf<unsigned long long> peer_delta;   // group ctx: device table of every member's delta buffer (fused all-reduce + apply)
 };
 
 }  // namespace fms
@@ -130,6 +135,10 @@ struct fms_ctx {
     size_t smem_optin = 0;
     fms::AlsState als;
     fms::SvmState svm;
+    // fms_create(ids, n > 1): this ctx is a GROUP -- one single-GPU member ctx per device (csrc/group.cu); compute state lives
+    // in the members, the parent only sequences them
+    std::vector<fms_ctx *> members;
+    std::vector<cudaEvent_t> member_ev;
 };
 
 namespace fms {
@@ -144,6 +153,14 @@ inline int fail(fms_ctx *ctx, int code, const char *fmt, ...) {
     if (ctx) ctx->err = buf;
     return code;
 }
+
+// NVTX range for the phases of a fit (the reference has no tracing beyond wall-clock prints)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 #define FMS_CUDA(ctx, expr)                                                                              \
     do {                                                                                                 \
@@ -216,7 +233,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---- internal entry points implemented across translation units ----
-int als_build_csr(fms_ctx *ctx, const int64_t *h_user, const int64_t *h_item, const double *h_rating, int64_t nnz);
+int als_build_csr(fms_ctx *ctx, const int64_t *h_user, const int64_t *h_item, const double *h_rating, int64_t nnz, int shard_index,
+                  int shard_count);
 int als_launch_init(fms_ctx *ctx, int64_t seed);
 int als_launch_half_step_generic(fms_ctx *ctx, int which, float lambda, int64_t row_begin, int64_t row_end);
 int als_tc_supported(const fms_ctx *ctx, int rank);
@@ -235,6 +253,13 @@ int als_tc_open_peers(fms_ctx *ctx, int s, const void *handles, int n);
 void als_tc_close_peers(fms_ctx *ctx, int s);
 int als_predict_device(fms_ctx *ctx, const int64_t *d_u, const int64_t *d_i, int64_t n, double *d_out, uint8_t *d_found);
 int als_ensure_fac64(fms_ctx *ctx);
+int group_create(fms_ctx *P, const int *device_ids, int n);
+void group_destroy(fms_ctx *P);
+int group_als_fit(fms_ctx *P, const int64_t *user, const int64_t *item, const double *rating, int64_t nnz, int rank, int iterations,
+                  double lambda, int64_t seed, int64_t *n_users, int64_t *n_items);
+int group_svm_fit(fms_ctx *P, const void *X, int x_dtype, const int64_t *csr_ptr, const int32_t *csr_idx, const double *y, int64_t n,
+                  int32_t dim, const int32_t *block_id, int blocks, int iterations, int64_t local_iterations, double regularization,
+                  double stepsize, int64_t seed, int rng_mode, double *w_out);
 int svm_launch_sweep(fms_ctx *ctx, int64_t local_iterations);
 int svm_launch_reduce_delta(fms_ctx *ctx);
 int svm_launch_apply(fms_ctx *ctx);

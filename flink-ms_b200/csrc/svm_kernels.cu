@@ -187,7 +187,7 @@ int svm_launch_sweep(fms_ctx *ctx, int64_t local_iterations) {
         FMS_CUDA(ctx, cudaMemcpyAsync(S.alpha_tmp.p, S.alpha.p, (size_t)S.n * sizeof(float), cudaMemcpyDeviceToDevice, st));
         alpha_work = S.alpha_tmp.p;
     }
-    const float lambda_n = (float)(S.lambda * (double)S.n);
+    const float lambda_n = (float)(S.lambda * (double)S.n_total);
     bool use_warp = false;
     if (S.kernel != FMS_SVM_KERNEL_GENERIC && S.rng_mode == FMS_RNG_PER_BLOCK) use_warp = svm_warp_supported(ctx) != 0;
     if (S.kernel == FMS_SVM_KERNEL_WARP && !use_warp)

@@ -194,7 +194,7 @@ int launch(fms_ctx *ctx, float *alpha_work, int64_t local_iterations) {
     if (n_local == 0) return FMS_OK;
     const size_t smem = (size_t)WARPS * STAGES * 128 * NV4 * 4 + WARPS * STAGES * 8;
     FMS_CUDA(ctx, cudaFuncSetAttribute(k_svm_sweep_warp<NV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const float lambda_n = (float)(S.lambda * (double)S.n);
+    const float lambda_n = (float)(S.lambda * (double)S.n_total);
     k_svm_sweep_warp<NV4><<<(n_local + WARPS - 1) / WARPS, WARPS * 32, smem, ctx->stream>>>(
         S.X, S.y.p, alpha_work, S.rows32.p, S.blk_ptr.p, S.d_local_blocks.p, n_local, (unsigned long long *)S.rng.p, S.w.p,
         S.dw_blocks.p, (long long)local_iterations, lambda_n);

@@ -8,8 +8,9 @@ trained by the CUDA kernels behind `operators.ALS` / `operators.SVM`, the rows a
 
 Differences a user should know: `--blocks` / `--temporaryPath` of the ALS job are accepted and have no effect (no Flink
 shuffles here); an output path is written as ONE text file (Flink writes a directory of part files at parallelism > 1);
-the SVM block of a row is `row_index * parallelism // n % blocks` with `--parallelism` (default 1) standing in for the
-Flink source parallelism that decides it in the reference.
+the SVM block of a row is FlinkMLTools.block's `LabeledVector.hashCode() % blocks` (flinkml_hash.py) and, at the default
+`--parallelism 1`, all blocks draw from ONE java.util.Random(seed ^ 0) in ascending block order like the single
+localDualMethod subtask of the reference.
 """
 from __future__ import annotations
 

@@ -19,6 +19,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _native as N
+from . import flinkml_hash as H
 
 
 class ParameterMap:
@@ -268,19 +269,35 @@ class SVM:
 
     @staticmethod
     def default_block_ids(n: int, blocks: int, parallelism: int = 1) -> np.ndarray:
-        """FlinkMLTools.block: blockID = sourceSubtaskIndex % blocks.  A file source hands each of the
-        `parallelism` subtasks one contiguous input split, so rows fall into contiguous chunks; with
-        parallelism 1 every row lands in block 0."""
-        split = (np.arange(n, dtype=np.int64) * parallelism) // max(n, 1)
-        return (split % blocks).astype(np.int32)
+        """The round-1 reading of FlinkMLTools.block (blockID = sourceSubtaskIndex % blocks); see
+        flinkml_hash.block_ids_by_subtask.  `fit` now defaults to the hash reading (block_mode="hash")."""
+        return H.block_ids_by_subtask(n, blocks, parallelism)
 
-    def fit(self, X, y=None, block_id=None, parallelism: int = 1, csr=None, dim=None, rng_mode=N.RNG_PER_BLOCK):
+    def fit(self, X, y=None, block_id=None, parallelism: int = 1, csr=None, dim=None, rng_mode=None, block_mode: str = "hash"):
         """X: dense (n x D) array, or csr=(ptr, idx, val) with dim; y in {+1,-1}.
-        block_id: explicit CoCoA block of every row; default mirrors FlinkMLTools.block at `parallelism`."""
+        block_id: explicit CoCoA block of every row.  Default (block_mode="hash"): FlinkMLTools.block as recollected by
+        the round-1 advisor and this author -- LabeledVector.hashCode() % blocks (flinkml_hash.py); block_mode="subtask"
+        is the round-1 reading.  rng_mode default: localDualMethod keeps ONE java.util.Random(seed ^ subtaskIndex) per
+        parallel subtask and the blocks of a subtask draw from it in ascending block order, so parallelism 1 means the
+        shared stream (RNG_SHARED_SUBTASK) and parallelism >= blocks one stream per block (RNG_PER_BLOCK); the cases in
+        between (several blocks on some subtasks, not all) are not covered by either schedule and are refused."""
         n = len(y)
         blocks = self._p["blocks"] if self._p["blocks"] is not None else parallelism
         if block_id is None:
-            block_id = SVM.default_block_ids(n, blocks, parallelism)
+            if block_mode == "hash":
+                block_id = H.block_ids_by_hash(y, blocks, X=X, csr=csr, dim=dim)
+            elif block_mode == "subtask":
+                block_id = H.block_ids_by_subtask(n, blocks, parallelism)
+            else:
+                raise ValueError("block_mode must be 'hash' or 'subtask'")
+        if rng_mode is None:
+            if parallelism <= 1 or blocks == 1:
+                rng_mode = N.RNG_SHARED_SUBTASK if blocks > 1 else N.RNG_PER_BLOCK
+            elif parallelism >= blocks:
+                rng_mode = N.RNG_PER_BLOCK
+            else:
+                raise NotImplementedError("1 < parallelism < blocks: blocks share per-subtask random streams in a pattern neither "
+                                          "RNG schedule of the C-ABI reproduces; pass rng_mode explicitly")
         seed = self._p["seed"]
         if seed is None:
             seed = random.getrandbits(63) - (1 << 62)   # FlinkML default: Random.nextLong()

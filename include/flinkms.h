@@ -10,8 +10,8 @@
  *   - return 0 (FMS_OK) or a negative fms_status; the message is fms_last_error(ctx) (ctx-owned, valid
  *     until the next call on that ctx).  The JNI shim turns non-zero into a RuntimeException.
  *   - caller owns every in/out HOST buffer; pointers are never retained past the call.
- *   - the library owns all device memory inside fms_ctx.  A ctx is bound to ONE GPU (one process per GPU;
- *     multi-GPU runs use one ctx per rank and exchange the device buffers exposed below with NCCL).
+ *   - the library owns all device memory inside fms_ctx.  A ctx is bound to ONE GPU, or -- fms_create with n_devices > 1 --
+ *     is a group that drives several GPUs from one process (see fms_create).
  *   - a ctx is NOT thread-safe (the reference calls fit once from the driver thread, ALSImpl.scala:52,
  *     and uses one lookup helper per operator thread, SGD.java:137, MSE.java:112).
  *   - there is NO CPU fallback: without a CUDA device every compute entry point returns FMS_ERR_CUDA.
@@ -62,7 +62,15 @@ enum { FMS_SVM_KERNEL_AUTO = 0, FMS_SVM_KERNEL_GENERIC = 1, FMS_SVM_KERNEL_WARP 
 /* ------------------------------------------------------------------------------------------------
  * context
  * ---------------------------------------------------------------------------------------------- */
-/* n_devices must be 1 (one process per GPU).  device_ids may be NULL => current device. */
+/* n_devices == 1: a ctx bound to one GPU (device_ids may be NULL => current device); every entry point below works on it.
+ * n_devices  > 1: a GROUP ctx -- ONE process (the JVM of a Flink task manager, a C program) drives n GPUs of one NVLink node:
+ *   the whole-fit entry points (fms_als_fit, fms_svm_fit) shard the rows / blocks over the devices inside the library (triples
+ *   and rows travel 1/n per device over PCIe, factor rows and the SVM delta between the GPUs over NVLink, device-side event
+ *   barriers between half-steps; no NCCL, no torch), and every entry point that reads the fitted model (get_factors, predict,
+ *   mse, sgd_step, get_weights, svm_predict, the parsers) is served by the first device, which holds the full model.  The
+ *   step-level entry points (fms_als_load .. fms_als_planes_*, fms_svm_load .. fms_svm_apply_delta) return
+ *   FMS_ERR_UNSUPPORTED on a group ctx: they exist for hosts that run one process per GPU.
+ *   This is how the reference's `setBlocks` / Flink parallelism (ALSImpl.scala:39-41, SVMImpl.scala:25) maps onto one box. */
 FMS_API int fms_create(fms_ctx **out, const int *device_ids, int n_devices);
 FMS_API void fms_destroy(fms_ctx *ctx);
 FMS_API const char *fms_last_error(const fms_ctx *ctx);
@@ -133,8 +141,8 @@ FMS_API int fms_parse_libsvm(fms_ctx *ctx, const char *text, int64_t nbytes, dou
 
 /* --- step-level ALS API: data resident in HBM, used by bench.py (`value`) and by the one-process-per-GPU
  *     sharded driver (flink-ms_b200/dist.py), which all-gathers the factor shards between half-steps. --- */
-/* Upload + index the ratings.  Every rank holds the full CSR pair and full factor replicas and SOLVES only
- * rows [shard_index*S, (shard_index+1)*S) with S = ceil(N / shard_count).  user / item / rating may be host OR
+/* Upload + index the ratings.  Every rank holds full factor replicas, the sorted distinct ids of both sides and the CSR of
+ * the rows it SOLVES: [shard_index*S, (shard_index+1)*S) with S = ceil(N / shard_count) (rows of other shards are empty).  user / item / rating may be host OR
  * device pointers (a sharded host uploads 1/G of the triples per rank and all-gathers them over NVLink first). */
 FMS_API int fms_als_load(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t nnz,
                          int shard_index, int shard_count, /*out*/ int64_t *n_users, int64_t *n_items);

@@ -66,6 +66,8 @@ def lib():
         L.orc_jrand_bounded.argtypes = [C.c_int64, C.c_int32, C.c_int, _i32p]
         L.orc_jrand_doubles.argtypes = [C.c_int64, C.c_int, _f64p]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_switch.argtypes = [C.c_char_p, C.c_int]
+        L.orc_get_switch.argtypes = [C.c_char_p]
         _lib = L
     return _lib
 
@@ -91,6 +93,23 @@ def jrand_doubles(seed: int, n: int) -> np.ndarray:
     out = np.empty(n, np.float64)
     lib().orc_jrand_doubles(seed, n, _p(out, _f64p))
     return out
+
+
+SWITCHES = ("als_lambda_times_n", "als_final_user_step", "svm_scaling_configured_blocks", "svm_alpha_scale_stepsize")
+
+
+def set_switch(name: str, value: int) -> None:
+    """Risk-register switch of the restatement (flinkml_oracle.c header): recollected details of FlinkML 1.3.1 that change
+    results.  Process-global; tests restore the default (1) after use."""
+    if lib().orc_set_switch(name.encode(), int(value)) != 0:
+        raise KeyError(name)
+
+
+def get_switch(name: str) -> int:
+    v = lib().orc_get_switch(name.encode())
+    if v < 0:
+        raise KeyError(name)
+    return v
 
 
 def num_threads() -> int:

@@ -29,6 +29,30 @@
 #define ORC_API __attribute__((visibility("default")))
 
 /* ------------------------------------------------------------------------------------------
+ * Risk register: every point of SURVEY.md Appendix A that is RECOLLECTED (not readable in
+ * /root/reference) and changes results is a named switch.  Defaults = the reading this oracle
+ * (and the CUDA path) implements; tests/test_oracle.py checks what each switch does, and
+ * tools/make_flink_goldens.sh produces the Flink 1.3.1 outputs that would pin them.
+ *   als_lambda_times_n   1: diag += lambda * n_u (ALS-WR, Zhou et al.)     0: diag += lambda
+ *   als_final_user_step  1: one extra users half-step after the loop       0: none
+ *   svm_scaling_configured_blocks
+ *                        1: dw scaled by stepsize / configured blocks      0: / non-empty blocks
+ *   svm_alpha_scale_stepsize
+ *                        1: alpha += stepsize * dAlpha                     0: alpha += (stepsize / blocks) * dAlpha
+ * (SVM block membership -- hash vs source subtask -- and the RNG schedule are explicit inputs.)
+ * ---------------------------------------------------------------------------------------- */
+static struct { int als_lambda_times_n, als_final_user_step, svm_scaling_configured_blocks, svm_alpha_scale_stepsize; } g_sw = {1, 1, 1, 1};
+static int *sw_slot(const char *name) {
+    if (!strcmp(name, "als_lambda_times_n")) return &g_sw.als_lambda_times_n;
+    if (!strcmp(name, "als_final_user_step")) return &g_sw.als_final_user_step;
+    if (!strcmp(name, "svm_scaling_configured_blocks")) return &g_sw.svm_scaling_configured_blocks;
+    if (!strcmp(name, "svm_alpha_scale_stepsize")) return &g_sw.svm_alpha_scale_stepsize;
+    return NULL;
+}
+ORC_API int orc_set_switch(const char *name, int value) { int *p = sw_slot(name); if (!p) return -1; *p = value; return 0; }
+ORC_API int orc_get_switch(const char *name) { int *p = sw_slot(name); return p ? *p : -1; }
+
+/* ------------------------------------------------------------------------------------------
  * java.util.Random  (scala.util.Random(seed) wraps it)
  * ---------------------------------------------------------------------------------------- */
 typedef struct { uint64_t s; } jrand;
@@ -235,7 +259,7 @@ ORC_API int64_t orc_als_half_step_range(orc_als *h, int which, double lambda, in
             int pos = 0;                                       /* generateFullMatrix */
             for (int row = 0; row < d; ++row)
                 for (int c = 0; c <= row; ++c) { full[row * d + c] = xtx[pos]; full[c * d + row] = xtx[pos]; ++pos; }
-            for (int f = 0; f < d; ++f) full[f * d + f] += lambda * (double)n;
+            for (int f = 0; f < d; ++f) full[f * d + f] += g_sw.als_lambda_times_n ? lambda * (double)n : lambda;
             if (chol_solve(full, xy, d)) ++bad;
             memcpy(T + u * d, xy, (size_t)d * sizeof(double));
         }
@@ -255,7 +279,7 @@ ORC_API int64_t orc_als_fit(orc_als *h, int rank, int iterations, double lambda,
         bad += orc_als_half_step(h, 0, lambda, nthreads);
         bad += orc_als_half_step(h, 1, lambda, nthreads);
     }
-    bad += orc_als_half_step(h, 0, lambda, nthreads);
+    if (g_sw.als_final_user_step) bad += orc_als_half_step(h, 0, lambda, nthreads);
     return bad;
 }
 ORC_API void orc_als_get_factors(const orc_als *h, int which, int64_t *ids, double *factors) {
@@ -345,7 +369,7 @@ static inline void x_axpy(const xmat *m, int64_t row, double c, double *w, doubl
  * rows: the block's member rows in arrival order.  alpha: the block's persistent alpha (len nk).
  * Updates alpha (alpha += stepsize * dAlpha) and writes dw (len dim). */
 static void sdca_block_round(const xmat *m, const double *y, const int64_t *rows, int64_t nk, double *alpha,
-                             jrand *rng, int64_t H, double lambda, double n_total, double stepsize,
+                             jrand *rng, int64_t H, double lambda, double n_total, double alpha_scale,
                              const double *w0, double *w, double *dw, double *tmp_alpha, double *d_alpha) {
     const int D = m->dim;
     memcpy(w, w0, (size_t)D * sizeof(double));
@@ -368,7 +392,7 @@ static void sdca_block_round(const xmat *m, const double *y, const int64_t *rows
             d_alpha[idx] += da;
         }
     }
-    for (int64_t i = 0; i < nk; ++i) alpha[i] += d_alpha[i] * stepsize;
+    for (int64_t i = 0; i < nk; ++i) alpha[i] += d_alpha[i] * alpha_scale;
 }
 
 /*
@@ -404,7 +428,10 @@ ORC_API int orc_svm_fit(const void *X, int x_dtype, const int64_t *csr_ptr, cons
     jrand *rngs = malloc((size_t)blocks * sizeof(jrand));
     for (int k = 0; k < blocks; ++k) jr_seed(&rngs[k], seed ^ (int64_t)k);
     jrand shared; jr_seed(&shared, seed ^ 0);
-    const double scaling = stepsize / (double)blocks;
+    int nonempty = 0;
+    for (int k = 0; k < blocks; ++k) nonempty += cnt[k + 1] > cnt[k];
+    const double scaling = stepsize / (double)(g_sw.svm_scaling_configured_blocks ? blocks : (nonempty ? nonempty : 1));
+    const double alpha_scale = g_sw.svm_alpha_scale_stepsize ? stepsize : stepsize / (double)blocks;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -420,7 +447,7 @@ ORC_API int orc_svm_fit(const void *X, int x_dtype, const int64_t *csr_ptr, cons
                     if (nk == 0) { memset(dw, 0, (size_t)dim * sizeof(double)); continue; }   /* empty block: no map call */
                     int64_t H = local_iterations > 0 ? local_iterations : nk;
                     sdca_block_round(&m, y, rows + cnt[k], nk, alpha + cnt[k], &rngs[k], H, regularization, (double)n,
-                                     stepsize, w, wl, dw, tmpa + cnt[k], dalp + cnt[k]);
+                                     alpha_scale, w, wl, dw, tmpa + cnt[k], dalp + cnt[k]);
                 }
                 free(wl);
             }
@@ -432,7 +459,7 @@ ORC_API int orc_svm_fit(const void *X, int x_dtype, const int64_t *csr_ptr, cons
                 if (nk == 0) { memset(dw, 0, (size_t)dim * sizeof(double)); continue; }
                 int64_t H = local_iterations > 0 ? local_iterations : nk;
                 sdca_block_round(&m, y, rows + cnt[k], nk, alpha + cnt[k], &shared, H, regularization, (double)n,
-                                 stepsize, w, wl, dw, tmpa + cnt[k], dalp + cnt[k]);
+                                 alpha_scale, w, wl, dw, tmpa + cnt[k], dalp + cnt[k]);
             }
             free(wl);
         }

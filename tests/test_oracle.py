@@ -1,5 +1,6 @@
 """CPU tests of the oracle: java.util.Random KATs, C oracle vs the independent numpy restatement, linear-algebra
 and optimisation identities that do not depend on recollecting FlinkML."""
+import importlib
 import json
 import os
 
@@ -254,3 +255,89 @@ def test_svm_converges_to_the_hinge_svm_optimum_of_liblinear():
     wr = ref.coef_.ravel()
     pr = 0.5 * lam * float(wr @ wr) + float(np.maximum(0.0, 1.0 - y * (X @ wr)).mean())
     assert abs(primal - pr) <= 1e-3 * max(1.0, abs(pr))
+
+
+# ---------------------------------------------------------------------------------------------- risk register (recollected details)
+@pytest.fixture
+def restore_switches():
+    yield
+    for name in oracle.SWITCHES:
+        oracle.set_switch(name, 1)
+
+
+def test_switch_names_and_defaults():
+    assert all(oracle.get_switch(n) == 1 for n in oracle.SWITCHES)
+    with pytest.raises(KeyError):
+        oracle.set_switch("no_such_switch", 0)
+
+
+def test_switch_als_lambda_scaling_and_final_user_step(restore_switches):
+    synth = importlib.import_module("flink-ms_b200.synth")
+    u, i, r = synth.als_ratings(60, 40, 900, seed=3)
+    lam, d = 0.9, 6
+
+    def row_solution(o, row, weight_by_n):
+        ids_i, Y = o.factors(1)
+        sel = np.flatnonzero(u == o.factors(0)[0][row])
+        V = Y[np.searchsorted(ids_i, i[sel])]
+        A = V.T @ V + (lam * len(sel) if weight_by_n else lam) * np.eye(d)
+        return np.linalg.solve(A, V.T @ r[sel])
+
+    for weight_by_n in (1, 0):
+        oracle.set_switch("als_lambda_times_n", weight_by_n)
+        o = oracle.OracleALS(u, i, r)
+        o.fit(d, 2, lam, 42)
+        X = o.factors(0)[1]
+        for row in (0, 7, 31):
+            np.testing.assert_allclose(X[row], row_solution(o, row, weight_by_n), rtol=1e-9, atol=1e-12)
+    oracle.set_switch("als_lambda_times_n", 1)
+    # without the extra users half-step the returned users were solved against the PREVIOUS items
+    o1 = oracle.OracleALS(u, i, r); o1.fit(d, 2, lam, 42)
+    oracle.set_switch("als_final_user_step", 0)
+    o0 = oracle.OracleALS(u, i, r); o0.fit(d, 2, lam, 42)
+    np.testing.assert_array_equal(o0.factors(1)[1], o1.factors(1)[1])          # items: identical
+    assert np.abs(o0.factors(0)[1] - o1.factors(0)[1]).max() > 1e-6            # users: one half-step apart
+    o0.half_step(0, lam)
+    np.testing.assert_allclose(o0.factors(0)[1], o1.factors(0)[1], rtol=0, atol=0)
+
+
+def test_switch_svm_scaling_and_alpha_scale(restore_switches):
+    synth = importlib.import_module("flink-ms_b200.synth")
+    X, y, _ = synth.svm_data(120, 16, seed=4)
+    blocks = 6
+    bid = (np.arange(120) % 4).astype(np.int32)                               # blocks 4 and 5 stay empty
+    base = oracle.svm_fit(X, y, bid, blocks, 1, -1, 1.0, 1.0, 7, 0)
+    oracle.set_switch("svm_scaling_configured_blocks", 0)
+    eff = oracle.svm_fit(X, y, bid, blocks, 1, -1, 1.0, 1.0, 7, 0)
+    np.testing.assert_allclose(eff, base * (6.0 / 4.0), rtol=1e-12)          # one round from w = 0: only the scale differs
+    oracle.set_switch("svm_scaling_configured_blocks", 1)
+    w1, a1 = oracle.svm_fit(X, y, bid, blocks, 1, -1, 1.0, 0.5, 7, 0, return_alpha=True)
+    oracle.set_switch("svm_alpha_scale_stepsize", 0)
+    w0, a0 = oracle.svm_fit(X, y, bid, blocks, 1, -1, 1.0, 0.5, 7, 0, return_alpha=True)
+    np.testing.assert_allclose(w0, w1, rtol=1e-12)                            # the weights of round 1 do not see alpha's scale
+    np.testing.assert_allclose(a0 * blocks, a1, rtol=1e-12)                   # alpha += (stepsize / blocks) dAlpha vs stepsize dAlpha
+
+
+def test_flink_goldens_if_present():
+    """Pinned parity: tests/golden/flink_*.json come from real Flink 1.3.1 runs (tools/make_flink_goldens.sh).  No JVM has
+    been available so far, so the files do not exist and the oracle stays PARITY UNPINNED; the day they do, this test is
+    what pins it."""
+    import glob
+    import json
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "flink_*.json")))
+    if not files:
+        pytest.skip("no Flink-generated goldens (no JVM / flink-ml 1.3.1 in this image): parity unpinned")
+    for f in files:
+        gold = json.load(open(f))
+        if gold["kind"] == "als":
+            o = oracle.OracleALS(np.asarray(gold["user"]), np.asarray(gold["item"]), np.asarray(gold["rating"]))
+            o.fit(gold["rank"], gold["iterations"], gold["lambda"], gold["seed"])
+            for which, key in ((0, "user_factors"), (1, "item_factors")):
+                ids, F = o.factors(which)
+                want = np.asarray([gold[key][str(int(k))] for k in ids])
+                np.testing.assert_allclose(F, want, rtol=1e-9, atol=1e-12)
+        elif gold["kind"] == "svm":
+            w = oracle.svm_fit(np.asarray(gold["X"]), np.asarray(gold["y"]), np.asarray(gold["block_id"], np.int32), gold["blocks"],
+                               gold["iterations"], gold["local_iterations"], gold["regularization"], gold["stepsize"], gold["seed"],
+                               gold["rng_mode"])
+            np.testing.assert_allclose(w, np.asarray(gold["weights"]), rtol=1e-9, atol=1e-12)
