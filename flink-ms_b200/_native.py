@@ -64,6 +64,12 @@ SIGNATURES = {
     "fms_svm_set_weights": (C.c_int, [_vp, _f64p, C.c_int32]),
     "fms_svm_get_weights": (C.c_int, [_vp, _f64p, C.c_int32]),
     "fms_svm_get_alpha": (C.c_int, [_vp, _f64p, C.c_int64]),
+    "fms_als_stream_begin": (C.c_int, [_vp, C.c_int64]),
+    "fms_als_stream_append": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.c_int64]),
+    "fms_als_stream_fit": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_int64, _i64p, _i64p]),
+    "fms_svm_stream_begin": (C.c_int, [_vp, C.c_int64, C.c_int32]),
+    "fms_svm_stream_append": (C.c_int, [_vp, _vp, C.c_int, _f64p, _i32p, C.c_int64]),
+    "fms_svm_stream_fit": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double, C.c_int64, C.c_int, _f64p]),
     "fms_svm_load": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _i64p, _i32p, _f64p, C.c_int64, C.c_int32, _i32p, C.c_int,
                                C.c_int, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int]),
     "fms_svm_sweep": (C.c_int, [_vp, C.c_int64]),
@@ -173,6 +179,18 @@ class Context:
         nu, ni = C.c_int64(), C.c_int64()
         self._check(self._lib.fms_als_fit(self._h, _p(u, _i64p), _p(i, _i64p), _p(r, _f64p), len(u), rank, iterations,
                                           lam, seed, C.byref(nu), C.byref(ni)))
+        self._als_shape = (nu.value, ni.value, rank)
+        return nu.value, ni.value
+
+    def als_fit_stream(self, user, item, rating, rank, iterations, lam, seed, chunk=1 << 20):
+        """fms_als_fit fed through the chunked-upload entry points (what a JVM host with < 2 GiB direct buffers does)."""
+        u, i, r = _i64(user), _i64(item), _f64(rating)
+        self._check(self._lib.fms_als_stream_begin(self._h, len(u)))
+        for b in range(0, len(u), chunk):
+            e = min(len(u), b + chunk)
+            self._check(self._lib.fms_als_stream_append(self._h, _p(u[b:e], _i64p), _p(i[b:e], _i64p), _p(r[b:e], _f64p), e - b))
+        nu, ni = C.c_int64(), C.c_int64()
+        self._check(self._lib.fms_als_stream_fit(self._h, rank, iterations, lam, seed, C.byref(nu), C.byref(ni)))
         self._als_shape = (nu.value, ni.value, rank)
         return nu.value, ni.value
 
@@ -357,6 +375,25 @@ class Context:
         self._check(self._lib.fms_svm_fit(self._h, xp, dt, pp, ip, _p(y, _f64p), len(y), dim, _p(b, _i32p), blocks,
                                           iterations, local_iterations, regularization, stepsize, seed, rng_mode, _p(w, _f64p)))
         self._svm_n = len(y)
+        return w
+
+    def svm_fit_stream(self, X, y, block_id, blocks, iterations, local_iterations, regularization=1.0, stepsize=1.0, seed=0,
+                       rng_mode=RNG_PER_BLOCK, chunk_rows=1024):
+        """fms_svm_fit for dense rows fed through the chunked-upload entry points."""
+        X = np.ascontiguousarray(X if X.dtype == np.float32 else np.asarray(X, np.float64))
+        dt = X_DENSE_F32 if X.dtype == np.float32 else X_DENSE_F64
+        y = _f64(y)
+        b = np.ascontiguousarray(block_id, np.int32)
+        n, dim = X.shape
+        self._check(self._lib.fms_svm_stream_begin(self._h, n, dim))
+        for s in range(0, n, chunk_rows):
+            e = min(n, s + chunk_rows)
+            xs = np.ascontiguousarray(X[s:e])
+            self._check(self._lib.fms_svm_stream_append(self._h, xs.ctypes.data_as(_vp), dt, _p(y[s:e], _f64p), _p(b[s:e], _i32p), e - s))
+        w = np.empty(dim, np.float64)
+        self._check(self._lib.fms_svm_stream_fit(self._h, blocks, iterations, local_iterations, regularization, stepsize, seed, rng_mode,
+                                                 _p(w, _f64p)))
+        self._svm_n = n
         return w
 
     def svm_load(self, X, y, block_id, blocks, shard_index=0, shard_count=1, regularization=1.0, stepsize=1.0, seed=0,

@@ -1250,10 +1250,12 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
 #undef FMS_TC_LAUNCH
     } else {
         // v2: ring slots of KS x 16 ratings (one producer / issuer handshake per slot), ring depth and active solver warps per
-        // row-length regime: many short systems -> 2 x 16 ratings per slot, 7 slots (84 KB), 12 solver warps; few long ones ->
+        // row-length regime: many short systems -> 16 ratings per slot, 13 slots (78 KB), 12 solver warps; few long ones ->
         // 4 x 16 ratings per slot, 6 slots (144 KB of gathers in flight, 6 of the 7 producer warps active), 6 solver warps
         static const int dbg = getenv("FMS_TC_DBG") ? atoi(getenv("FMS_TC_DBG")) : 0;   // timing experiments (wrong results): see the kernel
-        const int ks = short_rows ? 2 : 4;
+        // (measured on cfg2: slots of 32 ratings raise the short-row half-step's no-solver floor from 8.8 to 10.7 ms -- every
+        // system pays the padding to a multiple of the slot -- while slots of 64 cut the long-row half-step from 5.8 to 4.3 ms)
+        const int ks = short_rows ? 1 : 4;
         FMS_TRY(ensure_stage_csr(ctx, which, rb, re, zero_row, grid, tc::KROWS * ks));
 #define FMS_TC2_LAUNCH(DUMPF, LDG, NS, NA, KSV, DUMP_PTR)                                                                               \
     do {                                                                                                                             \
@@ -1264,10 +1266,10 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
             m_pl, A.ptr[which].p, A.stage_ptr[which].p, A.colp[which].p, A.valp[which].p, A.cta_rows[which].p, A.fac[which].p, t_hi,  \
             lambda, rb, A.info.p, DUMP_PTR, peers, n_peers, p_hi, dbg);                                                              \
     } while (0)
-        if (dump && short_rows) FMS_TC2_LAUNCH(true, false, 7, 12, 2, dump);
+        if (dump && short_rows) FMS_TC2_LAUNCH(true, false, 13, 12, 1, dump);
         else if (dump) FMS_TC2_LAUNCH(true, false, 6, 6, 4, dump);
-        else if (short_rows && ldgsts) FMS_TC2_LAUNCH(false, true, 7, 12, 2, nullptr);
-        else if (short_rows) FMS_TC2_LAUNCH(false, false, 7, 12, 2, nullptr);
+        else if (short_rows && ldgsts) FMS_TC2_LAUNCH(false, true, 13, 12, 1, nullptr);
+        else if (short_rows) FMS_TC2_LAUNCH(false, false, 13, 12, 1, nullptr);
         else if (ldgsts) FMS_TC2_LAUNCH(false, true, 6, 6, 4, nullptr);
         else FMS_TC2_LAUNCH(false, false, 6, 6, 4, nullptr);
 #undef FMS_TC2_LAUNCH

@@ -16,9 +16,12 @@ static thread_local std::string g_create_error;
         if (e_ != cudaSuccess) return fail((ctx), FMS_ERR_CUDA, "cudaSetDevice(%d): %s", (ctx)->device, cudaGetErrorString(e_)); \
     } while (0)
 
+static int als_fit_loaded(fms_ctx *ctx, int rank, int iterations, double lambda, int64_t seed, int64_t nnz);
+static int svm_run_rounds(fms_ctx *ctx, int iterations, int64_t local_iterations, int32_t dim, double *w_out);
+
 extern "C" {
 
-FMS_API int fms_version(void) { return 100; }
+FMS_API int fms_version(void) { return 110; }
 
 FMS_API int fms_create(fms_ctx **out, const int *device_ids, int n_devices) {
     if (!out) return FMS_ERR_INVALID_ARG;
@@ -314,8 +317,13 @@ FMS_API int fms_als_fit(fms_ctx *ctx, const int64_t *user, const int64_t *item, 
     if (rank < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_fit: rank %d < 1", rank);
     NvtxRange nvtx_("fms.als.fit");
     // FMS_LOG_JSON=1: one JSON line per iteration on stderr (costs a stream synchronisation per iteration, off by default)
-    static const bool log_json = getenv("FMS_LOG_JSON") != nullptr;
     FMS_TRY(fms_als_load(ctx, user, item, rating, nnz, 0, 1, n_users, n_items));
+    return als_fit_loaded(ctx, rank, iterations, lambda, seed, nnz);
+}
+
+// init + iterate(T){ users; items } + final users on the ratings already indexed in the ctx
+static int als_fit_loaded(fms_ctx *ctx, int rank, int iterations, double lambda, int64_t seed, int64_t nnz) {
+    static const bool log_json = getenv("FMS_LOG_JSON") != nullptr;
     FMS_TRY(fms_als_init(ctx, rank, seed));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (log_json) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
@@ -746,6 +754,10 @@ FMS_API int fms_svm_fit(fms_ctx *ctx, const void *X, int x_dtype, const int64_t 
     if (iterations < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_fit: iterations < 0");
     if (!w_out) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_fit: w_out is null");
     FMS_TRY(fms_svm_load(ctx, X, x_dtype, 0, csr_ptr, csr_idx, y, n, dim, block_id, blocks, 0, 1, regularization, stepsize, seed, rng_mode));
+    return svm_run_rounds(ctx, iterations, local_iterations, dim, w_out);
+}
+
+static int svm_run_rounds(fms_ctx *ctx, int iterations, int64_t local_iterations, int32_t dim, double *w_out) {
     NvtxRange nvtx_("fms.svm.fit rounds");
     for (int t = 0; t < iterations; ++t) {
         NvtxRange nvtx_r("fms.svm.round (sweep + reduce + apply)");
@@ -753,6 +765,108 @@ FMS_API int fms_svm_fit(fms_ctx *ctx, const void *X, int x_dtype, const int64_t 
         FMS_TRY(svm_launch_apply(ctx));
     }
     return fms_svm_get_weights(ctx, w_out, dim);
+}
+
+// ====================================================================================================== chunked upload
+FMS_API int fms_als_stream_begin(fms_ctx *ctx, int64_t nnz_total) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_stream_begin");
+    CHECK_CTX(ctx);
+    if (nnz_total < 0 || nnz_total >= ((int64_t)1 << 31) * 8) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_stream_begin: nnz_total %lld", (long long)nnz_total);
+    auto &T = ctx->stream;
+    FMS_CUDA(ctx, T.u.alloc((size_t)nnz_total));
+    FMS_CUDA(ctx, T.i.alloc((size_t)nnz_total));
+    FMS_CUDA(ctx, T.r.alloc((size_t)nnz_total));
+    T.nnz_cap = nnz_total;
+    T.nnz_fill = 0;
+    return FMS_OK;
+}
+
+FMS_API int fms_als_stream_append(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t count) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_stream_append");
+    CHECK_CTX(ctx);
+    auto &T = ctx->stream;
+    if (T.nnz_cap < 0) return fail(ctx, FMS_ERR_STATE, "fms_als_stream_append: begin first");
+    if (count < 0 || (count > 0 && (!user || !item || !rating))) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_stream_append: null input or count < 0");
+    if (T.nnz_fill + count > T.nnz_cap) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_stream_append: %lld + %lld ratings exceed the announced %lld", (long long)T.nnz_fill, (long long)count, (long long)T.nnz_cap);
+    if (count) {
+        FMS_CUDA(ctx, cudaMemcpyAsync(T.u.p + T.nnz_fill, user, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
+        FMS_CUDA(ctx, cudaMemcpyAsync(T.i.p + T.nnz_fill, item, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
+        FMS_CUDA(ctx, cudaMemcpyAsync(T.r.p + T.nnz_fill, rating, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
+        FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // the caller may reuse its buffer for the next piece
+    }
+    T.nnz_fill += count;
+    return FMS_OK;
+}
+
+FMS_API int fms_als_stream_fit(fms_ctx *ctx, int rank, int iterations, double lambda, int64_t seed, int64_t *n_users, int64_t *n_items) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_stream_fit");
+    CHECK_CTX(ctx);
+    auto &T = ctx->stream;
+    if (T.nnz_cap < 0) return fail(ctx, FMS_ERR_STATE, "fms_als_stream_fit: begin first");
+    if (T.nnz_fill != T.nnz_cap) return fail(ctx, FMS_ERR_STATE, "fms_als_stream_fit: %lld of the announced %lld ratings appended", (long long)T.nnz_fill, (long long)T.nnz_cap);
+    if (iterations < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_stream_fit: iterations %d < 0", iterations);
+    if (rank < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_stream_fit: rank %d < 1", rank);
+    const int64_t nnz = T.nnz_fill;
+    int rc = fms_als_load(ctx, T.u.p, T.i.p, T.r.p, nnz, 0, 1, n_users, n_items);        // device pointers
+    T.u.release(); T.i.release(); T.r.release();
+    T.nnz_cap = -1; T.nnz_fill = 0;
+    if (rc != FMS_OK) return rc;
+    return als_fit_loaded(ctx, rank, iterations, lambda, seed, nnz);
+}
+
+FMS_API int fms_svm_stream_begin(fms_ctx *ctx, int64_t n_total, int32_t dim) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_stream_begin");
+    CHECK_CTX(ctx);
+    if (n_total < 0 || dim < 1 || n_total >= ((int64_t)1 << 31)) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_begin: n_total %lld dim %d", (long long)n_total, dim);
+    auto &T = ctx->stream;
+    FMS_CUDA(ctx, T.X.alloc((size_t)n_total * (size_t)dim));
+    T.y.clear(); T.bid.clear();
+    T.y.reserve((size_t)n_total); T.bid.reserve((size_t)n_total);
+    T.n_cap = n_total; T.n_fill = 0; T.dim = dim;
+    return FMS_OK;
+}
+
+FMS_API int fms_svm_stream_append(fms_ctx *ctx, const void *X_rows, int x_dtype, const double *y, const int32_t *block_id, int64_t rows) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_stream_append");
+    CHECK_CTX(ctx);
+    auto &T = ctx->stream;
+    if (T.n_cap < 0) return fail(ctx, FMS_ERR_STATE, "fms_svm_stream_append: begin first");
+    if (rows < 0 || (rows > 0 && (!X_rows || !y || !block_id))) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_append: null input or rows < 0");
+    if (x_dtype != FMS_X_DENSE_F32 && x_dtype != FMS_X_DENSE_F64) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_append: rows must be dense fp32 or fp64");
+    if (T.n_fill + rows > T.n_cap) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_append: %lld + %lld rows exceed the announced %lld", (long long)T.n_fill, (long long)rows, (long long)T.n_cap);
+    if (rows) {
+        float *dst = T.X.p + (size_t)T.n_fill * (size_t)T.dim;
+        const int64_t cnt = rows * (int64_t)T.dim;
+        if (x_dtype == FMS_X_DENSE_F32) {
+            FMS_CUDA(ctx, cudaMemcpyAsync(dst, X_rows, (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
+            FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        } else {
+            FMS_TRY(upload_f64_as_f32(ctx, static_cast<const double *>(X_rows), cnt, dst));
+        }
+        T.y.insert(T.y.end(), y, y + rows);
+        T.bid.insert(T.bid.end(), block_id, block_id + rows);
+    }
+    T.n_fill += rows;
+    return FMS_OK;
+}
+
+FMS_API int fms_svm_stream_fit(fms_ctx *ctx, int blocks, int iterations, int64_t local_iterations, double regularization, double stepsize,
+                               int64_t seed, int rng_mode, double *w_out) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_stream_fit");
+    CHECK_CTX(ctx);
+    auto &T = ctx->stream;
+    if (T.n_cap < 0) return fail(ctx, FMS_ERR_STATE, "fms_svm_stream_fit: begin first");
+    if (T.n_fill != T.n_cap) return fail(ctx, FMS_ERR_STATE, "fms_svm_stream_fit: %lld of the announced %lld rows appended", (long long)T.n_fill, (long long)T.n_cap);
+    if (iterations < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_fit: iterations < 0");
+    if (!w_out) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_fit: w_out is null");
+    const int64_t n = T.n_fill;
+    // the staged rows are used in place (they stay alive in the ctx until the next stream_begin)
+    FMS_TRY(fms_svm_load(ctx, T.X.p, FMS_X_DENSE_F32, 1, nullptr, nullptr, T.y.data(), n, T.dim, T.bid.data(), blocks, 0, 1, regularization,
+                         stepsize, seed, rng_mode));
+    T.n_cap = -1;
+    std::vector<double>().swap(T.y);
+    std::vector<int32_t>().swap(T.bid);
+    return svm_run_rounds(ctx, iterations, local_iterations, T.dim, w_out);
 }
 
 FMS_API int fms_svm_predict(fms_ctx *ctx, const void *X, int x_dtype, const int64_t *csr_ptr, const int32_t *csr_idx, int64_t n,

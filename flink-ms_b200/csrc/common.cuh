@@ -135,6 +135,17 @@ struct fms_ctx {
     size_t smem_optin = 0;
     fms::AlsState als;
     fms::SvmState svm;
+    // chunked upload (fms_*_stream_*): inputs staged in HBM piece by piece before a whole fit
+    struct {
+        fms::DevBuf<int64_t> u, i;
+        fms::DevBuf<double> r;
+        int64_t nnz_cap = -1, nnz_fill = 0;
+        fms::DevBuf<float> X;
+        std::vector<double> y;
+        std::vector<int32_t> bid;
+        int64_t n_cap = -1, n_fill = 0;
+        int32_t dim = 0;
+    } stream;
     // fms_create(ids, n > 1): this ctx is a GROUP -- one single-GPU member ctx per device (csrc/group.cu); compute state lives
     // in the members, the parent only sequences them
     std::vector<fms_ctx *> members;

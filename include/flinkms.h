@@ -204,6 +204,20 @@ FMS_API int fms_svm_set_weights(fms_ctx *ctx, const double *w, int32_t dim);
 FMS_API int fms_svm_get_weights(fms_ctx *ctx, double *w, int32_t dim);
 FMS_API int fms_svm_get_alpha(fms_ctx *ctx, double *alpha, int64_t n);
 
+/* --- chunked upload for hosts whose buffers are capped (a Java direct ByteBuffer holds < 2 GiB; BASELINE configs[1] is 2.4 GB of
+ *     triples, configs[3] 41 GB of rows): the same whole fits, fed in pieces -- begin, append x k, fit.  The pieces are staged in
+ *     HBM as they arrive (ALS: the COO triples; SVM: dense fp32 rows + labels + block ids), the host never holds the whole input
+ *     in one buffer, and the results are identical to the one-shot calls.  Single-device ctx only. --- */
+FMS_API int fms_als_stream_begin(fms_ctx *ctx, int64_t nnz_total);
+FMS_API int fms_als_stream_append(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t count);
+FMS_API int fms_als_stream_fit(fms_ctx *ctx, int rank, int iterations, double lambda, int64_t seed,
+                               /*out*/ int64_t *n_users, int64_t *n_items);
+/* X_rows: `rows` dense rows of `dim` values, x_dtype FMS_X_DENSE_F32 or FMS_X_DENSE_F64 (stored as fp32 on the device either way). */
+FMS_API int fms_svm_stream_begin(fms_ctx *ctx, int64_t n_total, int32_t dim);
+FMS_API int fms_svm_stream_append(fms_ctx *ctx, const void *X_rows, int x_dtype, const double *y, const int32_t *block_id, int64_t rows);
+FMS_API int fms_svm_stream_fit(fms_ctx *ctx, int blocks, int iterations, int64_t local_iterations, double regularization,
+                               double stepsize, int64_t seed, int rng_mode, /*out*/ double *w_out);
+
 /* --- step-level SVM API (HBM-resident; sharded: this rank sweeps blocks k with k % shard_count ==
  *     shard_index, the host all-reduces the delta buffer, every rank applies it). --- */
 /* X_is_device != 0: X (dense fp32 only) already lives on this ctx's GPU and is used in place. */

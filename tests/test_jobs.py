@@ -68,7 +68,13 @@ def test_svm_job_end_to_end(fms, ctx, tmp_path):
     dst = tmp_path / "model.txt"
     jobs.svm_impl(["--training", str(src), "--blocks", "3", "--iteration", "4", "--seed", "9", "--partition", "false", "--output", str(dst)], ctx=ctx)
     w_job = formats.parse_svm_rows(dst.read_text().splitlines(), dim=X.shape[1])
-    w_orc = oracle.svm_fit(X, y, np.zeros(len(y), np.int32), 3, 4, 10, 1.0, 1.0, 9)    # parallelism 1: every row in block 0
+    # FlinkMLTools.block: LabeledVector.hashCode() % blocks over the SparseVectors readLibSVM builds (dim = largest index seen);
+    # parallelism 1: the three blocks share the one java.util.Random(seed ^ 0) of the single localDualMethod subtask
+    H = importlib.import_module("flink-ms_b200.flinkml_hash")
+    ptr = np.arange(len(y) + 1, dtype=np.int64) * X.shape[1]                        # no exact zeros in N(0,1) samples: all 15 stored
+    bid = H.block_ids_by_hash(y, 3, csr=(ptr, np.tile(np.arange(X.shape[1], dtype=np.int32), len(y)), X.reshape(-1)), dim=X.shape[1])
+    assert len(set(bid.tolist())) == 3
+    w_orc = oracle.svm_fit(X, y, bid, 3, 4, 10, 1.0, 1.0, 9, 1)
     assert np.abs(w_job - w_orc).max() <= 1e-4 * max(1.0, np.abs(w_orc).max())
     assert dst.read_text().splitlines()[0].startswith("1,")                          # 1-based feature ids
     out = io.StringIO()

@@ -1,5 +1,6 @@
 """GPU parity tests for the CoCoA/SDCA SVM path against the fp64 oracle: sample-index streams bit-exact, weights
 within 1e-4 relative (BASELINE.json north_star), labels exact on margin-safe queries."""
+import importlib
 import json
 import os
 
@@ -175,3 +176,30 @@ def test_sharded_rounds_match_unsharded(fms, ctx):
     for c in ranks:
         assert rel_err(c.svm_get_weights(dim), want) <= W_TOL
         c.close()
+
+
+@pytest.mark.gpu
+def test_chunked_upload_equals_one_shot_fit(fms, ctx):
+    """fms_*_stream_*: what a JVM host whose direct ByteBuffers stay below 2 GiB calls; same results as the
+    one-shot entry points, bit for bit."""
+    synth = importlib.import_module("flink-ms_b200.synth")
+    X, y, _ = synth.svm_data(3000, 128, seed=8)
+    bid = (np.arange(3000) % 12).astype(np.int32)
+    w1 = ctx.svm_fit(X, y, bid, 12, 3, -1, 1.0, 1.0, 5)
+    w2 = ctx.svm_fit_stream(X, y, bid, 12, 3, -1, 1.0, 1.0, 5, chunk_rows=700)
+    np.testing.assert_array_equal(w1, w2)
+    w3 = ctx.svm_fit_stream(X.astype(np.float64), y, bid, 12, 3, -1, 1.0, 1.0, 5, chunk_rows=999)
+    np.testing.assert_array_equal(w1, w3)
+    u, i, r = synth.als_ratings(900, 300, 20000, seed=6)
+    for rank in (64, 10):
+        ctx.als_fit(u, i, r, rank, 2, 0.9, 42)
+        a = [ctx.als_get_factors(w)[1].copy() for w in (0, 1)]
+        ctx.als_fit_stream(u, i, r, rank, 2, 0.9, 42, chunk=3333)
+        b = [ctx.als_get_factors(w)[1] for w in (0, 1)]
+        np.testing.assert_array_equal(a[0], b[0])
+        np.testing.assert_array_equal(a[1], b[1])
+    with pytest.raises(fms.FlinkMSError):
+        ctx.als_fit_stream(u[:10], i[:10], r[:10], 0, 1, 0.9, 42)            # rank < 1
+    ctx._check(ctx._lib.fms_als_stream_begin(ctx._h, 5))
+    with pytest.raises(fms.FlinkMSError):                                      # fit before everything announced has arrived
+        ctx._check(ctx._lib.fms_als_stream_fit(ctx._h, 8, 1, 0.9, 42, None, None))
