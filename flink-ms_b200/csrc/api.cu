@@ -16,10 +16,10 @@ static thread_local std::string g_create_error;
         if (e_ != cudaSuccess) return fail((ctx), FMS_ERR_CUDA, "cudaSetDevice(%d): %s", (ctx)->device, cudaGetErrorString(e_)); \
     } while (0)
 
+extern "C" {
+
 static int als_fit_loaded(fms_ctx *ctx, int rank, int iterations, double lambda, int64_t seed, int64_t nnz);
 static int svm_run_rounds(fms_ctx *ctx, int iterations, int64_t local_iterations, int32_t dim, double *w_out);
-
-extern "C" {
 
 FMS_API int fms_version(void) { return 110; }
 
@@ -769,10 +769,10 @@ static int svm_run_rounds(fms_ctx *ctx, int iterations, int64_t local_iterations
 
 // ====================================================================================================== chunked upload
 FMS_API int fms_als_stream_begin(fms_ctx *ctx, int64_t nnz_total) {
-    GROUP_UNSUPPORTED(ctx, "fms_als_stream_begin");
+    GROUP_FORWARD(ctx, fms_als_stream_begin(m0, nnz_total));            // a group stages the triples on its first device
     CHECK_CTX(ctx);
     if (nnz_total < 0 || nnz_total >= ((int64_t)1 << 31) * 8) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_stream_begin: nnz_total %lld", (long long)nnz_total);
-    auto &T = ctx->stream;
+    auto &T = ctx->staged;
     FMS_CUDA(ctx, T.u.alloc((size_t)nnz_total));
     FMS_CUDA(ctx, T.i.alloc((size_t)nnz_total));
     FMS_CUDA(ctx, T.r.alloc((size_t)nnz_total));
@@ -782,9 +782,9 @@ FMS_API int fms_als_stream_begin(fms_ctx *ctx, int64_t nnz_total) {
 }
 
 FMS_API int fms_als_stream_append(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t count) {
-    GROUP_UNSUPPORTED(ctx, "fms_als_stream_append");
+    GROUP_FORWARD(ctx, fms_als_stream_append(m0, user, item, rating, count));
     CHECK_CTX(ctx);
-    auto &T = ctx->stream;
+    auto &T = ctx->staged;
     if (T.nnz_cap < 0) return fail(ctx, FMS_ERR_STATE, "fms_als_stream_append: begin first");
     if (count < 0 || (count > 0 && (!user || !item || !rating))) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_stream_append: null input or count < 0");
     if (T.nnz_fill + count > T.nnz_cap) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_stream_append: %lld + %lld ratings exceed the announced %lld", (long long)T.nnz_fill, (long long)count, (long long)T.nnz_cap);
@@ -799,9 +799,20 @@ FMS_API int fms_als_stream_append(fms_ctx *ctx, const int64_t *user, const int64
 }
 
 FMS_API int fms_als_stream_fit(fms_ctx *ctx, int rank, int iterations, double lambda, int64_t seed, int64_t *n_users, int64_t *n_items) {
-    GROUP_UNSUPPORTED(ctx, "fms_als_stream_fit");
+    if (ctx && !ctx->members.empty()) {
+        fms_ctx *m0 = ctx->members[0];
+        auto &T0 = m0->staged;
+        if (T0.nnz_cap < 0) return fail(ctx, FMS_ERR_STATE, "fms_als_stream_fit: begin first");
+        if (T0.nnz_fill != T0.nnz_cap) return fail(ctx, FMS_ERR_STATE, "fms_als_stream_fit: %lld of the announced %lld ratings appended", (long long)T0.nnz_fill, (long long)T0.nnz_cap);
+        if (iterations < 0 || rank < 1) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_stream_fit: rank %d iterations %d", rank, iterations);
+        const int rc = group_als_fit(ctx, T0.u.p, T0.i.p, T0.r.p, T0.nnz_fill, rank, iterations, lambda, seed, n_users, n_items);   // device pointers
+        cudaSetDevice(m0->device);
+        T0.u.release(); T0.i.release(); T0.r.release();
+        T0.nnz_cap = -1; T0.nnz_fill = 0;
+        return rc;
+    }
     CHECK_CTX(ctx);
-    auto &T = ctx->stream;
+    auto &T = ctx->staged;
     if (T.nnz_cap < 0) return fail(ctx, FMS_ERR_STATE, "fms_als_stream_fit: begin first");
     if (T.nnz_fill != T.nnz_cap) return fail(ctx, FMS_ERR_STATE, "fms_als_stream_fit: %lld of the announced %lld ratings appended", (long long)T.nnz_fill, (long long)T.nnz_cap);
     if (iterations < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_als_stream_fit: iterations %d < 0", iterations);
@@ -815,10 +826,18 @@ FMS_API int fms_als_stream_fit(fms_ctx *ctx, int rank, int iterations, double la
 }
 
 FMS_API int fms_svm_stream_begin(fms_ctx *ctx, int64_t n_total, int32_t dim) {
-    GROUP_UNSUPPORTED(ctx, "fms_svm_stream_begin");
-    CHECK_CTX(ctx);
+    if (!ctx) return FMS_ERR_INVALID_ARG;
     if (n_total < 0 || dim < 1 || n_total >= ((int64_t)1 << 31)) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_begin: n_total %lld dim %d", (long long)n_total, dim);
-    auto &T = ctx->stream;
+    if (!ctx->members.empty()) {
+        // a group scatters the rows over its members by block at fit time: stage them in host memory inside the library
+        auto &T = ctx->staged;
+        try { T.hX.clear(); T.hX.reserve((size_t)n_total * (size_t)dim); } catch (const std::bad_alloc &) { return fail(ctx, FMS_ERR_OOM, "fms_svm_stream_begin: host staging of %lld x %d floats", (long long)n_total, dim); }
+        T.y.clear(); T.bid.clear();
+        T.n_cap = n_total; T.n_fill = 0; T.dim = dim;
+        return FMS_OK;
+    }
+    CHECK_CTX(ctx);
+    auto &T = ctx->staged;
     FMS_CUDA(ctx, T.X.alloc((size_t)n_total * (size_t)dim));
     T.y.clear(); T.bid.clear();
     T.y.reserve((size_t)n_total); T.bid.reserve((size_t)n_total);
@@ -827,13 +846,22 @@ FMS_API int fms_svm_stream_begin(fms_ctx *ctx, int64_t n_total, int32_t dim) {
 }
 
 FMS_API int fms_svm_stream_append(fms_ctx *ctx, const void *X_rows, int x_dtype, const double *y, const int32_t *block_id, int64_t rows) {
-    GROUP_UNSUPPORTED(ctx, "fms_svm_stream_append");
-    CHECK_CTX(ctx);
-    auto &T = ctx->stream;
+    if (!ctx) return FMS_ERR_INVALID_ARG;
+    auto &T = ctx->staged;
     if (T.n_cap < 0) return fail(ctx, FMS_ERR_STATE, "fms_svm_stream_append: begin first");
     if (rows < 0 || (rows > 0 && (!X_rows || !y || !block_id))) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_append: null input or rows < 0");
     if (x_dtype != FMS_X_DENSE_F32 && x_dtype != FMS_X_DENSE_F64) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_append: rows must be dense fp32 or fp64");
     if (T.n_fill + rows > T.n_cap) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_append: %lld + %lld rows exceed the announced %lld", (long long)T.n_fill, (long long)rows, (long long)T.n_cap);
+    if (!ctx->members.empty()) {
+        const size_t cnt = (size_t)rows * (size_t)T.dim;
+        if (x_dtype == FMS_X_DENSE_F32) T.hX.insert(T.hX.end(), static_cast<const float *>(X_rows), static_cast<const float *>(X_rows) + cnt);
+        else { const double *xd = static_cast<const double *>(X_rows); for (size_t q = 0; q < cnt; ++q) T.hX.push_back((float)xd[q]); }
+        T.y.insert(T.y.end(), y, y + rows);
+        T.bid.insert(T.bid.end(), block_id, block_id + rows);
+        T.n_fill += rows;
+        return FMS_OK;
+    }
+    CHECK_CTX(ctx);
     if (rows) {
         float *dst = T.X.p + (size_t)T.n_fill * (size_t)T.dim;
         const int64_t cnt = rows * (int64_t)T.dim;
@@ -852,13 +880,20 @@ FMS_API int fms_svm_stream_append(fms_ctx *ctx, const void *X_rows, int x_dtype,
 
 FMS_API int fms_svm_stream_fit(fms_ctx *ctx, int blocks, int iterations, int64_t local_iterations, double regularization, double stepsize,
                                int64_t seed, int rng_mode, double *w_out) {
-    GROUP_UNSUPPORTED(ctx, "fms_svm_stream_fit");
-    CHECK_CTX(ctx);
-    auto &T = ctx->stream;
+    if (!ctx) return FMS_ERR_INVALID_ARG;
+    auto &T = ctx->staged;
     if (T.n_cap < 0) return fail(ctx, FMS_ERR_STATE, "fms_svm_stream_fit: begin first");
     if (T.n_fill != T.n_cap) return fail(ctx, FMS_ERR_STATE, "fms_svm_stream_fit: %lld of the announced %lld rows appended", (long long)T.n_fill, (long long)T.n_cap);
     if (iterations < 0) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_fit: iterations < 0");
     if (!w_out) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_stream_fit: w_out is null");
+    if (!ctx->members.empty()) {
+        const int rc = group_svm_fit(ctx, T.hX.data(), FMS_X_DENSE_F32, nullptr, nullptr, T.y.data(), T.n_fill, T.dim, T.bid.data(), blocks, iterations,
+                                     local_iterations, regularization, stepsize, seed, rng_mode, w_out);
+        T.n_cap = -1;
+        std::vector<float>().swap(T.hX); std::vector<double>().swap(T.y); std::vector<int32_t>().swap(T.bid);
+        return rc;
+    }
+    CHECK_CTX(ctx);
     const int64_t n = T.n_fill;
     // the staged rows are used in place (they stay alive in the ctx until the next stream_begin)
     FMS_TRY(fms_svm_load(ctx, T.X.p, FMS_X_DENSE_F32, 1, nullptr, nullptr, T.y.data(), n, T.dim, T.bid.data(), blocks, 0, 1, regularization,

@@ -145,7 +145,8 @@ struct fms_ctx {
         std::vector<int32_t> bid;
         int64_t n_cap = -1, n_fill = 0;
         int32_t dim = 0;
-    } stream;
+        std::vector<float> hX;               // group ctx: rows staged on the host (they are scattered over the members at fit time)
+    } staged;
     // fms_create(ids, n > 1): this ctx is a GROUP -- one single-GPU member ctx per device (csrc/group.cu); compute state lives
     // in the members, the parent only sequences them
     std::vector<fms_ctx *> members;

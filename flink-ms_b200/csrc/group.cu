@@ -143,9 +143,10 @@ int group_als_fit(fms_ctx *P, const int64_t *user, const int64_t *item, const do
         if (e != cudaSuccess) { free_tmp(); return fail(P, FMS_ERR_OOM, "fms_als_fit: staging the triples on device %d: %s", m->device, cudaGetErrorString(e)); }
         const int64_t b = std::min<int64_t>(nnz, sl * g), c = std::min<int64_t>(nnz, sl * (g + 1)) - b;
         if (c > 0) {
-            cudaMemcpyAsync(du[(size_t)g] + b, user + b, (size_t)c * 8, cudaMemcpyHostToDevice, m->stream);
-            cudaMemcpyAsync(di[(size_t)g] + b, item + b, (size_t)c * 8, cudaMemcpyHostToDevice, m->stream);
-            cudaMemcpyAsync(dr[(size_t)g] + b, rating + b, (size_t)c * 8, cudaMemcpyHostToDevice, m->stream);
+            // cudaMemcpyDefault: the triples are host memory, or (chunked upload) already staged on the first device
+            cudaMemcpyAsync(du[(size_t)g] + b, user + b, (size_t)c * 8, cudaMemcpyDefault, m->stream);
+            cudaMemcpyAsync(di[(size_t)g] + b, item + b, (size_t)c * 8, cudaMemcpyDefault, m->stream);
+            cudaMemcpyAsync(dr[(size_t)g] + b, rating + b, (size_t)c * 8, cudaMemcpyDefault, m->stream);
         }
     }
     int rc = barrier_all(P);

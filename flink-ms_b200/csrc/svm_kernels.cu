@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_svm_sweep_generic(
     const float *__restrict__ cval, int x_kind, const float *__restrict__ y, float *__restrict__ alpha,
     const int64_t *__restrict__ rows, const int64_t *__restrict__ blk_ptr, const int32_t *__restrict__ local_blocks,
     unsigned long long *__restrict__ rng_state, int rng_shared, const float *__restrict__ w0, float *__restrict__ dw_out,
-    int dim, long long local_iterations, float lambda_n) {
+    int dim, long long local_iterations, float lambda_n, float inv_lambda_n) {
     extern __shared__ float sm[];
     float *w = sm, *dw = sm + dim, *red = sm + 2 * dim;
     const int lb = blockIdx.x;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_svm_sweep_generic(
             if (g != 0.f) {                                       // uniform across the CTA
                 const float an = (q != 0.f) ? fminf(fmaxf(a - g / q, 0.f), 1.f) : 1.f;
                 const float da = an - a;
-                const float c = yy * da / lambda_n;
+                const float c = yy * da * inv_lambda_n;      // the same fp32 reciprocal in every sweep kernel (svm_warp.cu)
                 if (x_kind == FMS_X_DENSE_F32) {
                     const float *x = X + row * (int64_t)dim;
                     for (int j = threadIdx.x; j < dim; j += blockDim.x) { const float t = c * x[j]; w[j] += t; dw[j] += t; }
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) k_svm_sweep_generic_shared(
     const float *__restrict__ cval, int x_kind, const float *__restrict__ y, float *__restrict__ alpha,
     const int64_t *__restrict__ rows, const int64_t *__restrict__ blk_ptr, int n_blocks,
     unsigned long long *__restrict__ rng_state, const float *__restrict__ w0, float *__restrict__ dw_out, int dim,
-    long long local_iterations, float lambda_n) {
+    long long local_iterations, float lambda_n, float inv_lambda_n) {
     extern __shared__ float sm[];
     float *w = sm, *dw = sm + dim, *red = sm + 2 * dim;
     JRand rng;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) k_svm_sweep_generic_shared(
             if (g != 0.f) {
                 const float an = (q != 0.f) ? fminf(fmaxf(a - g / q, 0.f), 1.f) : 1.f;
                 const float da = an - a;
-                const float c = yy * da / lambda_n;
+                const float c = yy * da * inv_lambda_n;      // the same fp32 reciprocal in every sweep kernel (svm_warp.cu)
                 if (x_kind == FMS_X_DENSE_F32) {
                     const float *x = X + row * (int64_t)dim;
                     for (int j = threadIdx.x; j < dim; j += blockDim.x) { const float t = c * x[j]; w[j] += t; dw[j] += t; }
@@ -187,7 +187,7 @@ int svm_launch_sweep(fms_ctx *ctx, int64_t local_iterations) {
         FMS_CUDA(ctx, cudaMemcpyAsync(S.alpha_tmp.p, S.alpha.p, (size_t)S.n * sizeof(float), cudaMemcpyDeviceToDevice, st));
         alpha_work = S.alpha_tmp.p;
     }
-    const float lambda_n = (float)(S.lambda * (double)S.n_total);
+    const float lambda_n = (float)(S.lambda * (double)S.n_total), inv_lambda_n = (float)(1.0 / (S.lambda * (double)S.n_total));
     bool use_warp = false;
     if (S.kernel != FMS_SVM_KERNEL_GENERIC && S.rng_mode == FMS_RNG_PER_BLOCK) use_warp = svm_warp_supported(ctx) != 0;
     if (S.kernel == FMS_SVM_KERNEL_WARP && !use_warp)
@@ -202,14 +202,14 @@ int svm_launch_sweep(fms_ctx *ctx, int64_t local_iterations) {
             FMS_CUDA(ctx, cudaFuncSetAttribute(k_svm_sweep_generic_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_svm_sweep_generic_shared<<<1, 256, smem, st>>>(S.X, S.csr_ptr.p, S.csr_idx.p, S.csr_val.p, S.x_kind, S.y.p, alpha_work,
                                                              S.rows.p, S.blk_ptr.p, S.blocks, (unsigned long long *)S.rng.p, S.w.p,
-                                                             S.dw_blocks.p, S.dim, (long long)local_iterations, lambda_n);
+                                                             S.dw_blocks.p, S.dim, (long long)local_iterations, lambda_n, inv_lambda_n);
             FMS_LAUNCH_CHECK(ctx);
         } else if (n_local > 0) {
             FMS_CUDA(ctx, cudaFuncSetAttribute(k_svm_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_svm_sweep_generic<<<n_local, 256, smem, st>>>(S.X, S.csr_ptr.p, S.csr_idx.p, S.csr_val.p, S.x_kind, S.y.p, alpha_work,
                                                             S.rows.p, S.blk_ptr.p, S.d_local_blocks.p,
                                                             (unsigned long long *)S.rng.p, 0, S.w.p, S.dw_blocks.p, S.dim,
-                                                            (long long)local_iterations, lambda_n);
+                                                            (long long)local_iterations, lambda_n, inv_lambda_n);
             FMS_LAUNCH_CHECK(ctx);
         }
     }

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_svm_sweep_warp(
     const float *__restrict__ X, const float *__restrict__ y, float *alpha, const int32_t *__restrict__ rows,
     const int64_t *__restrict__ blk_ptr, const int32_t *__restrict__ local_blocks, int n_local,
     unsigned long long *__restrict__ rng_state, const float *__restrict__ w0, float *__restrict__ dw_out,
-    long long local_iterations, float lambda_n) {
+    long long local_iterations, float lambda_n, float inv_lambda_n) {
     constexpr int D = 128 * NV4;
     constexpr uint32_t ROW_BYTES = D * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_svm_sweep_warp(
                 const float g = (y_cur * dot - 1.f) * lambda_n;
                 float a_new = a_cur;
                 if (g != 0.f) {
-                    a_new = (q != 0.f) ? fminf(fmaxf(a_cur - g / q, 0.f), 1.f) : 1.f;     // IEEE divides, exactly as k_svm_sweep_generic
-                    const float c = y_cur * (a_new - a_cur) / lambda_n;
+                    a_new = (q != 0.f) ? fminf(fmaxf(a_cur - g / q, 0.f), 1.f) : 1.f;     // IEEE divide (it decides the clip), as k_svm_sweep_generic
+                    const float c = y_cur * (a_new - a_cur) * inv_lambda_n;      // same expression as k_svm_sweep_generic
                     const float2 cc = make_float2(c, c);
 #pragma unroll
                     for (int v = 0; v < NV4; ++v) {
@@ -197,7 +197,7 @@ int launch(fms_ctx *ctx, float *alpha_work, int64_t local_iterations) {
     const float lambda_n = (float)(S.lambda * (double)S.n_total);
     k_svm_sweep_warp<NV4><<<(n_local + WARPS - 1) / WARPS, WARPS * 32, smem, ctx->stream>>>(
         S.X, S.y.p, alpha_work, S.rows32.p, S.blk_ptr.p, S.d_local_blocks.p, n_local, (unsigned long long *)S.rng.p, S.w.p,
-        S.dw_blocks.p, (long long)local_iterations, lambda_n);
+        S.dw_blocks.p, (long long)local_iterations, lambda_n, (float)(1.0 / (S.lambda * (double)S.n_total)));
     FMS_LAUNCH_CHECK(ctx);
     return FMS_OK;
 }

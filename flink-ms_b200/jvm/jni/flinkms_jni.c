@@ -21,12 +21,59 @@ static int check(JNIEnv *env, fms_ctx *ctx, int rc) {
     return rc;
 }
 
-JNIEXPORT jlong JNICALL Java_de_tub_it4bi_gpu_Native_create(JNIEnv *env, jclass cls, jint device) {
+JNIEXPORT jlong JNICALL Java_de_tub_it4bi_gpu_Native_create(JNIEnv *env, jclass cls, jintArray devices) {
     (void)cls;
     fms_ctx *ctx = NULL;
-    int dev = (int)device;
-    if (check(env, NULL, fms_create(&ctx, &dev, 1))) return 0;
+    int dev[64];
+    const jsize n = (*env)->GetArrayLength(env, devices);
+    if (n < 1 || n > 64) { check(env, NULL, FMS_ERR_INVALID_ARG); return 0; }
+    jint tmp[64];
+    (*env)->GetIntArrayRegion(env, devices, 0, n, tmp);
+    for (jsize k = 0; k < n; ++k) dev[k] = (int)tmp[k];
+    if (check(env, NULL, fms_create(&ctx, dev, (int)n))) return 0;      /* n > 1: a group ctx */
     return (jlong)(intptr_t)ctx;
+}
+
+/* chunked upload (direct ByteBuffers are capped at 2 GiB) */
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_alsStreamBegin(JNIEnv *env, jclass cls, jlong c, jlong nnz) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    check(env, ctx, fms_als_stream_begin(ctx, nnz));
+}
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_alsStreamAppend(JNIEnv *env, jclass cls, jlong c, jobject user, jobject item,
+                                                                    jobject rating, jlong count) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    check(env, ctx, fms_als_stream_append(ctx, buf(env, user), buf(env, item), buf(env, rating), count));
+}
+JNIEXPORT jlongArray JNICALL Java_de_tub_it4bi_gpu_Native_alsStreamFit(JNIEnv *env, jclass cls, jlong c, jint rank, jint iterations,
+                                                                       jdouble lambda, jlong seed) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    int64_t n[2] = {0, 0};
+    if (check(env, ctx, fms_als_stream_fit(ctx, rank, iterations, lambda, seed, &n[0], &n[1]))) return NULL;
+    jlongArray out = (*env)->NewLongArray(env, 2);
+    jlong v[2] = {(jlong)n[0], (jlong)n[1]};
+    if (out) (*env)->SetLongArrayRegion(env, out, 0, 2, v);
+    return out;
+}
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_svmStreamBegin(JNIEnv *env, jclass cls, jlong c, jlong n, jint dim) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    check(env, ctx, fms_svm_stream_begin(ctx, n, dim));
+}
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_svmStreamAppend(JNIEnv *env, jclass cls, jlong c, jobject x, jint xDtype, jobject y,
+                                                                    jobject blockId, jlong rows) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    check(env, ctx, fms_svm_stream_append(ctx, buf(env, x), xDtype, buf(env, y), buf(env, blockId), rows));
+}
+JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_svmStreamFit(JNIEnv *env, jclass cls, jlong c, jint blocks, jint iterations,
+                                                                 jlong localIterations, jdouble regularization, jdouble stepsize,
+                                                                 jlong seed, jint rngMode, jobject w) {
+    (void)cls;
+    fms_ctx *ctx = (fms_ctx *)(intptr_t)c;
+    check(env, ctx, fms_svm_stream_fit(ctx, blocks, iterations, localIterations, regularization, stepsize, seed, rngMode, buf(env, w)));
 }
 
 JNIEXPORT void JNICALL Java_de_tub_it4bi_gpu_Native_destroy(JNIEnv *env, jclass cls, jlong ctx) {

@@ -25,16 +25,26 @@ class ALS {
   def fit(input: DataSet[(Int, Int, Double)], fitParameters: ParameterMap): Unit = {
     val p = parameters ++ fitParameters
     val rank = p(ALS.NumFactors); val iters = p(ALS.Iterations); val lambda = p(ALS.Lambda); val seed = p(ALS.Seed)
-    // one GPU task drains the DataSet into direct buffers, calls fms_als_fit, emits (which, id, factors)
+    // one GPU task drains the DataSet in pieces of CHUNK triples (a direct ByteBuffer holds < 2 GiB; configs[1] is 2.4 GB)
+    // through the chunked-upload entry points, fits, emits (which, id, factors).  Devices: -Dflinkms.devices=0[,1,...]
     val rows: DataSet[(Int, Long, Array[Double])] = input.mapPartition { it =>
       val triples = it.toArray
       val n = triples.length
-      def direct(bytes: Long) = ByteBuffer.allocateDirect(bytes.toInt).order(ByteOrder.nativeOrder())
-      val (u, i, r) = (direct(8L * n), direct(8L * n), direct(8L * n))
-      triples.foreach { t => u.putLong(t._1.toLong); i.putLong(t._2.toLong); r.putDouble(t._3) }
-      val gpu = new Native(0)
+      val CHUNK = 1 << 24
+      def direct(bytes: Long) = { require(bytes < Int.MaxValue, "direct buffer over 2 GiB"); ByteBuffer.allocateDirect(bytes.toInt).order(ByteOrder.nativeOrder()) }
+      val (u, i, r) = (direct(8L * CHUNK), direct(8L * CHUNK), direct(8L * CHUNK))
+      val gpu = Native.fromProperties()
       try {
-        val counts = gpu.alsFit(u, i, r, n, rank, iters, lambda, seed)
+        gpu.alsStreamBegin(n)
+        var b = 0
+        while (b < n) {
+          val e = math.min(n, b + CHUNK)
+          u.clear(); i.clear(); r.clear()
+          var k = b; while (k < e) { val t = triples(k); u.putLong(t._1.toLong); i.putLong(t._2.toLong); r.putDouble(t._3); k += 1 }
+          gpu.alsStreamAppend(u, i, r, e - b)
+          b = e
+        }
+        val counts = gpu.alsStreamFit(rank, iters, lambda, seed)
         (0 to 1).iterator.flatMap { which =>
           val cnt = counts(which).toInt
           val ids = direct(8L * cnt); val fac = direct(8L * cnt * rank)

@@ -68,6 +68,7 @@ enum { FMS_SVM_KERNEL_AUTO = 0, FMS_SVM_KERNEL_GENERIC = 1, FMS_SVM_KERNEL_WARP 
  *   and rows travel 1/n per device over PCIe, factor rows and the SVM delta between the GPUs over NVLink, device-side event
  *   barriers between half-steps; no NCCL, no torch), and every entry point that reads the fitted model (get_factors, predict,
  *   mse, sgd_step, get_weights, svm_predict, the parsers) is served by the first device, which holds the full model.  The
+ *   The chunked-upload entry points (fms_*_stream_*) work on a group too.  The
  *   step-level entry points (fms_als_load .. fms_als_planes_*, fms_svm_load .. fms_svm_apply_delta) return
  *   FMS_ERR_UNSUPPORTED on a group ctx: they exist for hosts that run one process per GPU.
  *   This is how the reference's `setBlocks` / Flink parallelism (ALSImpl.scala:39-41, SVMImpl.scala:25) maps onto one box. */
@@ -207,7 +208,8 @@ FMS_API int fms_svm_get_alpha(fms_ctx *ctx, double *alpha, int64_t n);
 /* --- chunked upload for hosts whose buffers are capped (a Java direct ByteBuffer holds < 2 GiB; BASELINE configs[1] is 2.4 GB of
  *     triples, configs[3] 41 GB of rows): the same whole fits, fed in pieces -- begin, append x k, fit.  The pieces are staged in
  *     HBM as they arrive (ALS: the COO triples; SVM: dense fp32 rows + labels + block ids), the host never holds the whole input
- *     in one buffer, and the results are identical to the one-shot calls.  Single-device ctx only. --- */
+ *     in one buffer, and the results are identical to the one-shot calls.  On a group ctx the triples are staged on the first
+ *     device and the SVM rows in host memory owned by the library (they are scattered over the devices by block at fit time). --- */
 FMS_API int fms_als_stream_begin(fms_ctx *ctx, int64_t nnz_total);
 FMS_API int fms_als_stream_append(fms_ctx *ctx, const int64_t *user, const int64_t *item, const double *rating, int64_t count);
 FMS_API int fms_als_stream_fit(fms_ctx *ctx, int rank, int iterations, double lambda, int64_t seed,

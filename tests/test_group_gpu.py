@@ -54,6 +54,20 @@ def test_group_svm_fit_matches_single_gpu(fms, ctx, group):
     assert np.abs(w1 - w2).max() <= 1e-6 * max(np.abs(w1).max(), 1e-30)
 
 
+def test_group_chunked_upload(fms, ctx, group):
+    synth = importlib.import_module("flink-ms_b200.synth")
+    u, i, r = synth.als_ratings(1500, 400, 40000, seed=12)
+    ctx.als_fit(u, i, r, 64, 2, 0.9, 42)
+    group.als_fit_stream(u, i, r, 64, 2, 0.9, 42, chunk=7001)
+    for which in (0, 1):
+        np.testing.assert_array_equal(ctx.als_get_factors(which)[1], group.als_get_factors(which)[1])
+    X, y, _ = synth.svm_data(2000, 128, seed=9)
+    bid = (np.arange(2000) % 10).astype(np.int32)
+    w1 = group.svm_fit(X, y, bid, 10, 3, -1, 1.0, 1.0, 3)
+    w2 = group.svm_fit_stream(X, y, bid, 10, 3, -1, 1.0, 1.0, 3, chunk_rows=333)
+    np.testing.assert_array_equal(w1, w2)
+
+
 def test_group_refuses_step_level_calls(fms, group):
     with pytest.raises(fms.FlinkMSError) as e:
         group.als_half_step(0, 0.9)

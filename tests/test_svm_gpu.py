@@ -90,14 +90,24 @@ def test_shared_subtask_rng_and_empty_blocks(fms, ctx):
 
 
 def test_reference_default_shape_one_partition(fms, ctx):
-    """BASELINE configs[0]-style run: parallelism 1 => all rows in block 0, blocks=10 only scales the step
-    (SVMImpl.scala:24-26 with FlinkML defaults H=10, lambda=1, stepsize=1)."""
+    """BASELINE configs[0]-style run (SVMImpl.scala:24-26 with FlinkML defaults H=10, lambda=1, stepsize=1) at parallelism 1:
+    FlinkMLTools.block hashes the rows over the 10 blocks (flinkml_hash.py) and the single localDualMethod subtask draws all
+    blocks' samples from ONE java.util.Random(seed ^ 0), ascending block order.  The round-1 reading (all rows in block 0, the
+    block count only scaling the step) stays available as block_mode="subtask"."""
+    import importlib
+    H = importlib.import_module("flink-ms_b200.flinkml_hash")
     X, y, _ = fms.synth.svm_data(1000, 32, seed=8)
     svm = fms.SVM(ctx).setBlocks(10).setIterations(10).setSeed(42)
     svm.fit(X, y)
-    want = oracle.svm_fit(X, y, np.zeros(1000, np.int32), 10, 10, 10, 1.0, 1.0, 42, 0)
+    bid = H.block_ids_by_hash(y, 10, X=X)
+    assert len(set(bid.tolist())) == 10
+    want = oracle.svm_fit(X, y, bid, 10, 10, 10, 1.0, 1.0, 42, 1)
     w = svm.weightsOption[0].data
     assert rel_err(w, want) <= W_TOL
+    svm1 = fms.SVM(ctx).setBlocks(10).setIterations(10).setSeed(42)
+    svm1.fit(X, y, block_mode="subtask")
+    want1 = oracle.svm_fit(X, y, np.zeros(1000, np.int32), 10, 10, 10, 1.0, 1.0, 42, 0)
+    assert rel_err(svm1.weightsOption[0].data, want1) <= W_TOL
     # SVMImpl.scala:33-35: weights -> (1-based feature id, value)
     model = [(j + 1, v) for j, v in enumerate(w)]
     assert model[0][0] == 1 and len(model) == 32
