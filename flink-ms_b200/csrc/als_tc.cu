@@ -756,8 +756,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_als_rows_tc64(
 //     stage a DRAM gather) trades solver buffers for a deeper ring -- gathers in flight are what paces it (Little's law:
 //     13 stages x 6 KB against ~2.5 us of loaded DRAM latency is one stage per ~200 cycles).
 // 24 warps: epilogue 0-3 | solvers 4-15 | MMA 16 | producers 17-23.
-constexpr int V2_WARPS = 24, V2_W_SOLVE0 = 4, V2_N_SOLVE = 12, V2_W_MMA = 16, V2_W_PROD0 = 17;
-constexpr int V2_REGS_EPI = 72, V2_REGS_SOLVE = 104, V2_REGS_AUX = 40;     // (4 x 72 + 12 x 104 + 8 x 40) x 32 <= 768 x 80
+// Warp roles are a template parameter set: NSW solver warps after the 4 epilogue warps, then the MMA issuer, then NP producers
+// (the rest of the last warpgroup idles).  Register budgets (setmaxnreg, per warpgroup) must fit the launch allocation 768 x 80:
+//   long rows : 12 solver warps x 104 + 4 x 72 + 8 x 40   (6 solver buffers in use: few systems, many stages)
+//   short rows: 16 solver warps x  96 + 4 x 56 + 4 x 40   (the solvers pace this half-step: every warp that fits is one)
+constexpr int V2_WARPS = 24, V2_W_SOLVE0 = 4;
+constexpr int V2_REGS_AUX = 40;
 using TL4 = cm::Tiles<4>;
 constexpr int V2_BUF_FLOATS = TL4::FLOATS + 3 * D;                          // tiles | bz | invd | xs  per solver warp
 
@@ -790,7 +794,7 @@ __device__ __forceinline__ void tc_ld16x256_x1(uint32_t taddr, float (&v)[4]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <bool DUMP, bool LDGSTS, int NSTG_, int NSA, int KS, int NP>
+template <bool DUMP, bool LDGSTS, int NSTG_, int NSA, int KS, int NP, int NSW>
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64_v2(
     const __grid_constant__ CUtensorMap map_pl, const int64_t *__restrict__ ptr,
     const int32_t *__restrict__ stage_ptr, const int32_t *__restrict__ colp, const float *__restrict__ valp,
@@ -798,10 +802,14 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64_v2(
     int64_t row_begin, int *__restrict__ info, float *__restrict__ dump, __half *const *__restrict__ peers, int n_peers,
     const __half *__restrict__ S_pl, int dbg) {
     using SM = Smem2<NSTG_, NSA, KS>;
+    constexpr int V2_W_MMA = V2_W_SOLVE0 + NSW, V2_W_PROD0 = V2_W_MMA + 1;
+    constexpr int V2_REGS_EPI = NSW > 12 ? 56 : 72, V2_REGS_SOLVE = NSW > 12 ? 96 : 104;
+    static_assert(NSW % 4 == 0 && V2_W_PROD0 + NP <= V2_WARPS && NSA <= NSW, "warp roles");
+    static_assert((N_EPI * V2_REGS_EPI + NSW * V2_REGS_SOLVE + (V2_WARPS - N_EPI - NSW) * V2_REGS_AUX) <= V2_WARPS * 80, "register budgets");
     // Parity waits tell adjacent phases apart only: a producer may run at most one ring revolution ahead of the issuer.  Its
     // previous stage was NP stages back and legitimately within NSTG_ of the issuer, so NSTG_ >= NP keeps it inside two
     // phases (with 6 slots and 7 producers the seventh stage's producer passed its wait two phases early: mbarrier overflow).
-    static_assert(NSTG_ >= NP && NP <= N_PROD, "ring depth must cover the active producers");
+    static_assert(NSTG_ >= NP, "ring depth must cover the active producers");
     constexpr int STG = KS * STAGE_BYTES;                       // one ring slot: KS sub-stages of 16 ratings (one handshake per slot)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
@@ -1250,28 +1258,28 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
 #undef FMS_TC_LAUNCH
     } else {
         // v2: ring slots of KS x 16 ratings (one producer / issuer handshake per slot), ring depth and active solver warps per
-        // row-length regime: many short systems -> 16 ratings per slot, 13 slots (78 KB), 12 solver warps; few long ones ->
+        // row-length regime: many short systems -> 16 ratings per slot, 7 slots, 3 producers, 16 solver warps; few long ones ->
         // 4 x 16 ratings per slot, 6 slots (144 KB of gathers in flight, 6 of the 7 producer warps active), 6 solver warps
         static const int dbg = getenv("FMS_TC_DBG") ? atoi(getenv("FMS_TC_DBG")) : 0;   // timing experiments (wrong results): see the kernel
         // (measured on cfg2: slots of 32 ratings raise the short-row half-step's no-solver floor from 8.8 to 10.7 ms -- every
         // system pays the padding to a multiple of the slot -- while slots of 64 cut the long-row half-step from 5.8 to 4.3 ms)
         const int ks = short_rows ? 1 : 4;
         FMS_TRY(ensure_stage_csr(ctx, which, rb, re, zero_row, grid, tc::KROWS * ks));
-#define FMS_TC2_LAUNCH(DUMPF, LDG, NS, NA, KSV, DUMP_PTR)                                                                               \
+#define FMS_TC2_LAUNCH(DUMPF, LDG, NS, NA, KSV, NPV, NSWV, DUMP_PTR)                                                                    \
     do {                                                                                                                             \
-        constexpr int NPV = NS < tc::N_PROD ? NS : tc::N_PROD;                                                                        \
         const size_t smem = (size_t)tc::Smem2<NS, NA, KSV>::total + 1024;                                                             \
-        FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64_v2<DUMPF, LDG, NS, NA, KSV, NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        tc::k_als_rows_tc64_v2<DUMPF, LDG, NS, NA, KSV, NPV><<<grid, tc::V2_WARPS * 32, smem, ctx->stream>>>(                          \
+        FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64_v2<DUMPF, LDG, NS, NA, KSV, NPV, NSWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        tc::k_als_rows_tc64_v2<DUMPF, LDG, NS, NA, KSV, NPV, NSWV><<<grid, tc::V2_WARPS * 32, smem, ctx->stream>>>(                    \
             m_pl, A.ptr[which].p, A.stage_ptr[which].p, A.colp[which].p, A.valp[which].p, A.cta_rows[which].p, A.fac[which].p, t_hi,  \
             lambda, rb, A.info.p, DUMP_PTR, peers, n_peers, p_hi, dbg);                                                              \
     } while (0)
-        if (dump && short_rows) FMS_TC2_LAUNCH(true, false, 13, 12, 1, dump);
-        else if (dump) FMS_TC2_LAUNCH(true, false, 6, 6, 4, dump);
-        else if (short_rows && ldgsts) FMS_TC2_LAUNCH(false, true, 13, 12, 1, nullptr);
-        else if (short_rows) FMS_TC2_LAUNCH(false, false, 13, 12, 1, nullptr);
-        else if (ldgsts) FMS_TC2_LAUNCH(false, true, 6, 6, 4, nullptr);
-        else FMS_TC2_LAUNCH(false, false, 6, 6, 4, nullptr);
+        //                                  DUMP   LDGSTS slots bufs KS NP NSW
+        if (dump && short_rows) FMS_TC2_LAUNCH(true, false, 7, 16, 1, 3, 16, dump);
+        else if (dump) FMS_TC2_LAUNCH(true, false, 6, 6, 4, 6, 12, dump);
+        else if (short_rows && ldgsts) FMS_TC2_LAUNCH(false, true, 7, 16, 1, 3, 16, nullptr);
+        else if (short_rows) FMS_TC2_LAUNCH(false, false, 7, 16, 1, 3, 16, nullptr);
+        else if (ldgsts) FMS_TC2_LAUNCH(false, true, 6, 6, 4, 6, 12, nullptr);
+        else FMS_TC2_LAUNCH(false, false, 6, 6, 4, 6, 12, nullptr);
 #undef FMS_TC2_LAUNCH
     }
     FMS_LAUNCH_CHECK(ctx);
