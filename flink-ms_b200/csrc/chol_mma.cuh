@@ -36,8 +36,8 @@ namespace cm {
 __device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 // x ~= hi + lo with hi, lo representable in TF32 (22 mantissa bits together)
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
-    hi = tf32_rna(x);
-    lo = tf32_rna(x - __uint_as_float(hi));
+    hi = tf32_rna(x);                                             // masked: x - hi below must be exact
+    lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;      // + half an ulp; the tensor core's truncation completes the rounding
 }
 // A B fragment travels as ONE 64-bit value (b0 low, b1 high): ptxas then keeps it in the aligned register pair HMMA wants
 // (as two separate 32-bit variables every use cost two MOVs: ~1 000 of the prototype's 7 300 instructions per system).
@@ -94,14 +94,14 @@ struct Tiles {
 };
 
 // Solves one system in place.  S: tile layout (negated matrix) -- holds L afterwards.  bz: D floats, -b in, z out.
-// invd: D floats scratch (1 / L_jj).  xs: D floats scratch (x, for the broadcasts of the back substitution).
+// invd: D floats scratch (unused by the solver since W replaces the diagonal blocks; kept for the caller's staging).  xs: D floats scratch (x, for the broadcasts of the back substitution).
 // x_out[q] = x[lane + 32 q].  All four arrays are private to the calling warp; the caller provides the barrier that
 // made S and bz visible (mbarrier wait or __syncwarp).
 template <int MT>
 __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__restrict__ bz, float *__restrict__ invd, float *__restrict__ xs,
                                             const int lane, float (&x_out)[MT / 2]) {
     using TL = Tiles<MT>;
-    constexpr int D = TL::D, NT = TL::NT;
+    constexpr int NT = TL::NT;
     const int g = lane >> 2, t = lane & 3;
     float4 *S4 = reinterpret_cast<float4 *>(S);
     BFrag bh[NT], bl[NT];                                   // B fragments (hi / lo) of the current panel's L, per n-tile
@@ -113,6 +113,7 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
         const int Id = J >> 1, h = J & 1;
         // ---- 1. diagonal block, factored redundantly: a[r (r + 1) / 2 + c] = (A + lambda n I)[8 J + r][8 J + c], c <= r
         BFrag wb_h, wb_l;
+        float2 w_own;
         {
             const float *Td = S + (Id * (Id + 1) + J) * 128 + 2 * h;
             float a[36];
@@ -135,10 +136,6 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
 #pragma unroll
                     for (int i = j; i < 8; ++i) a[i * (i + 1) / 2 + j] = fmaf(-a[i * (i + 1) / 2 + k], a[j * (j + 1) / 2 + k], a[i * (i + 1) / 2 + j]);
             }
-            if (lane == 0) {
-                *reinterpret_cast<float4 *>(invd + 8 * J) = make_float4(rinv[0], rinv[1], rinv[2], rinv[3]);
-                *reinterpret_cast<float4 *>(invd + 8 * J + 4) = make_float4(rinv[4], rinv[5], rinv[6], rinv[7]);
-            }
             // row g of W = Ld^-1 (w Ld = e_g^T, solved from the right; entries right of the diagonal come out 0)
             float wv[8];
 #pragma unroll
@@ -150,8 +147,9 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
             }
             // B fragment of -W: n = g (row of W), k slot t -> column 2 t, k slot t + 4 -> column 2 t + 1
             uint32_t h0, l0, h1, l1;
-            split_tf32(-sel4(t, wv[0], wv[2], wv[4], wv[6]), h0, l0);
-            split_tf32(-sel4(t, wv[1], wv[3], wv[5], wv[7]), h1, l1);
+            w_own = make_float2(sel4(t, wv[0], wv[2], wv[4], wv[6]), sel4(t, wv[1], wv[3], wv[5], wv[7]));   // W[g][2t], W[g][2t+1]
+            split_tf32(-w_own.x, h0, l0);
+            split_tf32(-w_own.y, h1, l1);
             wb_h = bfrag(h0, h1);
             wb_l = bfrag(l0, l1);
         }
@@ -175,16 +173,30 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
                 af.set(L.x, L.y, L.z, L.w);
                 bh[2 * I] = bfrag(af.h0, af.h2); bl[2 * I] = bfrag(af.l0, af.l2);                  // rows g     -> n-tile 2 I
                 bh[2 * I + 1] = bfrag(af.h1, af.h3); bl[2 * I + 1] = bfrag(af.l1, af.l3);          // rows g + 8 -> n-tile 2 I + 1
-                // descending j with an early exit: a real (uniform) branch instead of predicated-off HMMA / LDS / STS
+                // descending j in PAIRS with an early exit (a real, uniform branch instead of predicated-off HMMA / LDS / STS):
+                // the two tiles' 3-HMMA chains are independent, so interleaving them fills the ~30-cycle dependent-issue gaps
+                // (one tile at a time, ptxas pads every HMMA of the chain with a NOP)
 #pragma unroll
-                for (int j = 2 * I + 1; j >= 0; --j) {
+                for (int j = 2 * I + 1; j >= 1; j -= 2) {
                     if (j <= J) break;
-                    float4 c = S4[(I * (I + 1) + j) * 32 + lane];
-                    mma3(c, af, bh[j], bl[j]);
-                    S4[(I * (I + 1) + j) * 32 + lane] = c;
+                    const bool two = j - 1 > J;                         // the lower tile of the pair is live too
+                    float4 c0 = S4[(I * (I + 1) + j) * 32 + lane];
+                    float4 c1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (two) c1 = S4[(I * (I + 1) + j - 1) * 32 + lane];
+                    mma_tf32(c0, af.l0, af.l1, af.l2, af.l3, bh[j]);
+                    mma_tf32(c1, af.l0, af.l1, af.l2, af.l3, bh[j - 1]);
+                    mma_tf32(c0, af.h0, af.h1, af.h2, af.h3, bl[j]);
+                    mma_tf32(c1, af.h0, af.h1, af.h2, af.h3, bl[j - 1]);
+                    mma_tf32(c0, af.h0, af.h1, af.h2, af.h3, bh[j]);
+                    mma_tf32(c1, af.h0, af.h1, af.h2, af.h3, bh[j - 1]);
+                    S4[(I * (I + 1) + j) * 32 + lane] = c0;
+                    if (two) S4[(I * (I + 1) + j - 1) * 32 + lane] = c1;
                 }
             }
         }
+        // the diagonal block of the factor is only ever used through its inverse again (back substitution): keep W = Ld^-1 there.
+        // Lane (g, t) owns exactly the two entries W[g][2t], W[g][2t+1] of its fragment position.
+        *reinterpret_cast<float2 *>(S + (Id * (Id + 1) + J) * 128 + lane * 4 + 2 * h) = w_own;
         // ---- 4. right-hand-side row (row D of the matrix): z_J = bz_J (-W)^T, bz_j += z_J L(j, J)^T
         {
             float2 bv = make_float2(0.f, 0.f);
@@ -211,7 +223,8 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
         __syncwarp();
     }
 
-    // ---- back substitution L^T x = z: column i = lane + 32 q per lane, pivots in groups of four, blocks of 32 columns descending
+    // ---- back substitution L^T x = z: column i = lane + 32 q per lane, one panel (8 pivots) at a time, blocks of 32 columns
+    // descending.  x_J = W_J^T r_J with W_J = Ld^-1 stored over the diagonal block: no sequential triangular solve.
     constexpr int NQ = MT / 2;
     float zq[NQ];
 #pragma unroll
@@ -221,26 +234,27 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
     for (int q = NQ - 1; q >= 0; --q) {
         float x = 0.f;
 #pragma unroll 1
-        for (int jr = 28; jr >= 0; jr -= 4) {
-            const int j0 = 32 * q + jr;
-            const float z0 = __shfl_sync(0xffffffffu, zq[q], jr), z1 = __shfl_sync(0xffffffffu, zq[q], jr + 1);
-            const float z2 = __shfl_sync(0xffffffffu, zq[q], jr + 2), z3 = __shfl_sync(0xffffffffu, zq[q], jr + 3);
-            // rows j0 .. j0 + 3 share m-tile and half; element (j0 + r, i) at rb + 16 r + (column part)
-            const int I = j0 >> 4;
-            const int rb = (I * (I + 1)) * 128 + (j0 & 7) * 16 + ((j0 >> 3) & 1) * 2;
-            const int cb = rb + (j0 >> 3) * 128 + ((j0 & 7) >> 1) * 4;                  // column j0 (even): columns j0 + c at + (c >> 1) * 4 + (c & 1)
-            const float l10 = S[cb + 16], l20 = S[cb + 32], l21 = S[cb + 32 + 1], l30 = S[cb + 48], l31 = S[cb + 48 + 1], l32 = S[cb + 48 + 4];
-            const float4 iv = *reinterpret_cast<const float4 *>(invd + j0);
-            const float v3 = z3 * iv.w;
-            const float v2 = fmaf(-l32, v3, z2) * iv.z;
-            const float v1 = fmaf(-l31, v3, fmaf(-l21, v2, z1)) * iv.y;
-            const float v0 = fmaf(-l30, v3, fmaf(-l20, v2, fmaf(-l10, v1, z0))) * iv.x;
+        for (int jr = 24; jr >= 0; jr -= 8) {
+            const int j0 = 32 * q + jr, J = j0 >> 3, I = J >> 1, hh = J & 1;
             const int rel = lane - jr;
-            if (rel >= 0 && rel < 4) x = sel4(rel, v0, v1, v2, v3);
-            if (rel < 0) {                                            // columns left of the group: z_i -= sum_c L[j0 + c][i] x_c
-                const float *p = S + rb + 4 * q * 128 + lp;
-                zq[q] = fmaf(-p[48], v3, fmaf(-p[32], v2, fmaf(-p[16], v1, fmaf(-p[0], v0, zq[q]))));
+            // pivot lane c = rel: x_c = sum_r W[r][c] r_r  (W lower triangular, zeros above the diagonal are stored)
+            const float *wc = S + (I * (I + 1) + J) * 128 + 2 * hh + ((rel & 7) >> 1) * 4 + (rel & 1);
+            float xc = 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float zr = __shfl_sync(0xffffffffu, zq[q], jr + r);
+                xc = fmaf(wc[16 * r], zr, xc);
             }
+            if (rel >= 0 && rel < 8) x = xc;
+            // columns left of the panel: z_i -= sum_c L[j0 + c][i] x_c
+            const float *p = S + (I * (I + 1)) * 128 + 2 * hh + 4 * q * 128 + lp;
+            float acc = zq[q];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float xv = __shfl_sync(0xffffffffu, xc, jr + c);
+                acc = fmaf(-p[16 * c], xv, acc);
+            }
+            if (rel < 0) zq[q] = acc;
         }
         x_out[q] = x;
         if (q > 0) {
