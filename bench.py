@@ -229,7 +229,7 @@ def workload_config(args, world, p2p):
         par = "1 GPU"
     elif p2p:
         par = (f"rows sharded over {world} GPUs, one process per GPU; solver warps store each new gather-plane row into every "
-               f"replica over NVLink (CUDA IPC peer mappings), one cross-rank barrier per half-step")
+               f"replica over NVLink (CUDA IPC peer mappings), the half-step kernels order themselves with epoch flags in the replicas (release/acquire at system scope) -- no host collective between half-steps")
     else:
         par = f"rows sharded over {world} GPUs, one process per GPU; NCCL all-gather of the solved shard after every half-step"
     return {"workload": f"ALS rank={args.rank}, {args.users} users x {args.items} items, {args.nnz} synthetic ratings "

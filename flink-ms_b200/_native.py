@@ -56,6 +56,7 @@ SIGNATURES = {
     "fms_als_planes_open_peers": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
     "fms_als_planes_updated": (C.c_int, [_vp, C.c_int]),
     "fms_als_planes_peer_count": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)]),
+    "fms_als_planes_flag_sync": (C.c_int, [_vp, C.c_int]),
     "fms_als_last_info": (C.c_int, [_vp, _i64p]),
     "fms_als_set_kernel": (C.c_int, [_vp, C.c_int]),
     "fms_svm_fit": (C.c_int, [_vp, _vp, C.c_int, _i64p, _i32p, _f64p, C.c_int64, C.c_int32, _i32p, C.c_int, C.c_int,
@@ -256,6 +257,9 @@ class Context:
 
     def als_planes_open_peers(self, which, handles: bytes, n: int):
         self._check(self._lib.fms_als_planes_open_peers(self._h, which, C.c_char_p(handles) if n else None, n))
+
+    def als_planes_flag_sync(self, enable: bool):
+        self._check(self._lib.fms_als_planes_flag_sync(self._h, 1 if enable else 0))
 
     def als_planes_peer_count(self, which) -> int:
         n = C.c_int()

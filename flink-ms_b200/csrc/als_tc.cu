@@ -192,6 +192,25 @@ constexpr int V2_REGS_AUX = 40;
 using TL4 = cm::Tiles<4>;
 constexpr int V2_BUF_FLOATS = TL4::FLOATS + 3 * D;                          // tiles | bz | invd | xs  per solver warp
 
+// Cross-rank ordering of the half-steps when the solver warps store into every replica (one process per GPU, planes mapped over
+// CUDA IPC): no host-side collective.  The LAST CTA of a half-step on side s publishes epoch e into slot [my_rank] of the flag
+// words kept in the spare rows of EVERY replica's side-s plane buffer (system-scope release after all of the rank's remote
+// stores); a half-step that reads side s first waits until all `n` slots of its LOCAL flag words reached the epoch it expects.
+// Seeing every rank's flag also means every rank FINISHED that half-step, so the replicas may be overwritten by the next one.
+struct FlagSync {
+    int *ctr;                  // per-ctx counter of finished CTAs (last-block detection)
+    const int *wait_flags;     // local flag words of the side being READ (partner), or nullptr: nothing to wait for
+    int wait_epoch;
+    int64_t signal_off;        // offset (in halves) of the flag words inside the plane buffer of the side being WRITTEN
+    int signal_epoch, my_rank, n;
+};
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
 template <int NSTG_, int NSA, int KS>
 struct Smem2 {
     static constexpr int ring = 0;
@@ -227,7 +246,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
     const int32_t *__restrict__ stage_ptr, const int32_t *__restrict__ colp, const float *__restrict__ valp,
     const int32_t *__restrict__ cta_rows, float *__restrict__ T, __half *__restrict__ T_pl, float lambda,
     int64_t row_begin, int *__restrict__ info, float *__restrict__ dump, __half *const *__restrict__ peers, int n_peers,
-    const __half *__restrict__ S_pl, int dbg) {
+    const __half *__restrict__ S_pl, int dbg, FlagSync fs) {
     using SM = Smem2<NSTG_, NSA, KS>;
     constexpr int V2_W_MMA = V2_W_SOLVE0 + NSW, V2_W_PROD0 = V2_W_MMA + 1;
     constexpr int V2_REGS_EPI = NSW > 12 ? 56 : 72, V2_REGS_SOLVE = NSW > 12 ? 96 : 104;
@@ -262,6 +281,11 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
     if (warp == V2_W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sm_base + SM::tmem_ptr) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (fs.wait_flags != nullptr && threadIdx.x == 0) {
+        // every rank's rows of the side this half-step gathers from have landed in OUR replica (and every rank is done with it)
+        for (int r = 0; r < fs.n; ++r)
+            while (ld_acquire_sys(fs.wait_flags + r) < fs.wait_epoch) {}
     }
     fence_proxy_async();                                           // the zero fill must be visible to the tensor core
     tc_fence_before();
@@ -489,6 +513,15 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
     if (warp == V2_W_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
+    if (fs.ctr != nullptr && threadIdx.x == 0) {
+        __threadfence_system();                                    // this CTA's remote plane stores before its count
+        if (atomicAdd(fs.ctr, 1) == (int)gridDim.x - 1) {          // last CTA of this rank's half-step
+            *fs.ctr = 0;
+            __threadfence_system();
+            for (int p = 0; p < fs.n; ++p)
+                st_release_sys(reinterpret_cast<int *>(peers[p] + fs.signal_off) + fs.my_rank, fs.signal_epoch);
+        }
+    }
 }
 
 // fp32 factor rows -> gather planes (after init, after an all-gather, after the generic kernel wrote a side)
@@ -566,6 +599,9 @@ int als_tc_supported(const fms_ctx *ctx, int rank) {
 
 // planes of side s: [hi: rows x 64 halves][lo: rows x 64 halves], rows = padded rows + 8 (row `padded` stays zero)
 static int64_t plane_rows(const AlsState &A, int s) { return A.shard_rows[s] * A.shard_count + 8; }
+// flag words of the in-kernel cross-rank ordering: spare row `padded + 4` of the plane buffer (row `padded` is the zero row the
+// stage padding gathers; 64 ints = one slot per rank)
+static int64_t flag_off_halves(const AlsState &A, int s) { return (A.shard_rows[s] * A.shard_count + 4) * (int64_t)tc::PLANE_PITCH; }
 
 static int ensure_planes(fms_ctx *ctx, int s) {
     AlsState &A = ctx->als;
@@ -673,6 +709,19 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
         // row-length regime: many short systems -> 16 ratings per slot, 7 slots, 3 producers, 16 solver warps; few long ones ->
         // 4 x 16 ratings per slot, 6 slots (144 KB of gathers in flight, 6 of the 7 producer warps active), 6 solver warps
         static const int dbg = getenv("FMS_TC_DBG") ? atoi(getenv("FMS_TC_DBG")) : 0;   // timing experiments (wrong results): see the kernel
+        // in-kernel cross-rank ordering (flag words in the spare rows of the plane buffers), only with mapped replicas of BOTH sides
+        tc::FlagSync fs = {nullptr, nullptr, 0, 0, 0, 0, 0};
+        if (n_peers > 0 && A.peer_n[partner] == n_peers && A.flag_sync) {
+            FMS_CUDA(ctx, A.sync_ctr.alloc(1));
+            if (!A.sync_ctr_zeroed) { FMS_CUDA(ctx, cudaMemsetAsync(A.sync_ctr.p, 0, sizeof(int), ctx->stream)); A.sync_ctr_zeroed = true; }
+            fs.ctr = A.sync_ctr.p;
+            fs.wait_flags = reinterpret_cast<const int *>(p_hi + flag_off_halves(A, partner));
+            fs.wait_epoch = A.plane_epoch[partner];
+            fs.signal_off = flag_off_halves(A, which);
+            fs.signal_epoch = ++A.plane_epoch[which];
+            fs.my_rank = A.shard_index;
+            fs.n = n_peers;
+        }
         // (measured on cfg2: slots of 32 ratings raise the short-row half-step's no-solver floor from 8.8 to 10.7 ms -- every
         // system pays the padding to a multiple of the slot -- while slots of 64 cut the long-row half-step from 5.8 to 4.3 ms)
         const int ks = short_rows ? 1 : 4;
@@ -683,7 +732,7 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
         FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<DUMPF, LDG, NS, NA, KSV, NPV, NSWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         tc::k_als_rows_tc64<DUMPF, LDG, NS, NA, KSV, NPV, NSWV><<<grid, tc::V2_WARPS * 32, smem, ctx->stream>>>(                    \
             m_pl, A.ptr[which].p, A.stage_ptr[which].p, A.colp[which].p, A.valp[which].p, A.cta_rows[which].p, A.fac[which].p, t_hi,  \
-            lambda, rb, A.info.p, DUMP_PTR, peers, n_peers, p_hi, dbg);                                                              \
+            lambda, rb, A.info.p, DUMP_PTR, peers, n_peers, p_hi, dbg, fs);                                                          \
     } while (0)
         //                                  DUMP   LDGSTS slots bufs KS NP NSW
         if (dump && short_rows) FMS_TC2_LAUNCH(true, false, 7, 16, 1, 3, 16, dump);
@@ -718,6 +767,7 @@ int als_tc_planes(fms_ctx *ctx, int s, void **hi, void **lo, int64_t *rows_padde
 // ---- peer-to-peer plane exchange (one process per GPU on one node): CUDA IPC handles in, device table of replicas out
 void als_tc_close_peers(fms_ctx *ctx, int s) {
     AlsState &A = ctx->als;
+    A.plane_epoch[s] = 0;
     for (int r = 0; r < A.peer_n[s]; ++r) {
         if (A.peer_open[s][r]) cudaIpcCloseMemHandle(A.peer_open[s][r]);
         A.peer_open[s][r] = nullptr;
@@ -759,6 +809,10 @@ int als_tc_open_peers(fms_ctx *ctx, int s, const void *handles, int n) {
     A.peer_n[s] = n;
     FMS_CUDA(ctx, A.peer_tab[s].alloc(64));
     FMS_CUDA(ctx, cudaMemcpyAsync(A.peer_tab[s].p, tab, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, ctx->stream));
+    // fresh flag words for the in-kernel ordering; the HOST must put one barrier across the ranks between this call and the
+    // first half-step (a peer's first signal must not be overwritten by this memset)
+    A.plane_epoch[s] = 0;
+    FMS_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<__half *>(A.plane[s].p) + flag_off_halves(A, s), 0, 64 * sizeof(int), ctx->stream));
     FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FMS_OK;
 }

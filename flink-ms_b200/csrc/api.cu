@@ -297,6 +297,13 @@ FMS_API int fms_als_planes_peer_count(fms_ctx *ctx, int which, int *n_peers) {
     return FMS_OK;
 }
 
+FMS_API int fms_als_planes_flag_sync(fms_ctx *ctx, int enable) {
+    GROUP_UNSUPPORTED(ctx, "fms_als_planes_flag_sync");
+    if (!ctx) return FMS_ERR_INVALID_ARG;
+    ctx->als.flag_sync = enable != 0;
+    return FMS_OK;
+}
+
 FMS_API int fms_als_planes_updated(fms_ctx *ctx, int which) {
     GROUP_UNSUPPORTED(ctx, "fms_als_planes_updated");
     if (!ctx) return FMS_ERR_INVALID_ARG;

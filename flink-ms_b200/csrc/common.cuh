@@ -75,6 +75,11 @@ struct AlsState {
     DevBuf<unsigned long long> peer_tab[2];
     void *peer_open[2][64] = {};
     int peer_n[2] = {0, 0};
+    // in-kernel cross-rank ordering of the half-steps (als_tc.cu FlagSync): epochs per side, last-CTA counter
+    int plane_epoch[2] = {0, 0};
+    bool flag_sync = false;                  // host opted in (fms_als_planes_flag_sync): it then needs no barrier between half-steps
+    DevBuf<int> sync_ctr;
+    bool sync_ctr_zeroed = false;
     // tensor-core path: ratings re-laid in 16-rating stages per row (padded), see als_tc.cu
     DevBuf<int32_t> stage_ptr[2];            // per row: first stage (exclusive scan of ceil(n_row / 16)), N + 1 entries
     DevBuf<int32_t> colp[2];                 // 16 * total_stages partner indices (padding -> zero row of the planes)

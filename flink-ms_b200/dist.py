@@ -112,6 +112,11 @@ class ContextALSBackend:
             table = table.cpu().numpy().reshape(world, 2, 64)
             for which in (0, 1):
                 self.ctx.als_planes_open_peers(which, table[:, which, :].tobytes(), world)
+            # fresh flag words on every rank before anybody's first half-step can signal into them
+            dist.all_reduce(torch.zeros(1, device=self.device), group=group)
+            torch.cuda.synchronize(self.device)
+        # the half-step kernels order themselves across the ranks (epoch flags in the replicas): no collective between them
+        self.ctx.als_planes_flag_sync(True)
         self.p2p = True
         return True
 
@@ -193,10 +198,9 @@ class DistributedALS:
 
     def half_step(self, which, lam):
         if self.world > 1 and getattr(self.b, "p2p", False):
-            # the kernel stored every solved plane row into all replicas over NVLink: only a barrier is left
+            # the kernel stored every solved plane row into all replicas over NVLink and published its epoch there; the next
+            # half-step waits for every rank's epoch inside the kernel (fms_als_planes_flag_sync): nothing to do on the host
             self.b.half_step(which, lam)
-            with torch.cuda.stream(self.b.stream):
-                dist.all_reduce(self._token(), group=self.group)
             self.b.planes_updated(which)
             self._stale.add(which)
             return

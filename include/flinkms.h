@@ -177,6 +177,13 @@ FMS_API int fms_als_planes_device(fms_ctx *ctx, int which, void **hi, void **lo,
 FMS_API int fms_als_planes_ipc_handle(fms_ctx *ctx, int which, void *handle64);
 FMS_API int fms_als_planes_open_peers(fms_ctx *ctx, int which, const void *handles, int n);
 FMS_API int fms_als_planes_updated(fms_ctx *ctx, int which);
+/* With the replicas of BOTH sides mapped, the half-step kernels can order themselves across the ranks: the last CTA of a rank's
+ * half-step publishes an epoch into flag words kept in every replica (system-scope release after the rank's remote stores), and a
+ * half-step first waits until all ranks published the epoch of the side it gathers from.  enable != 0 switches that on; the host
+ * then needs NO barrier or collective between half-steps (only fms_als_planes_updated).  Every rank must issue the same sequence
+ * of half-step calls, and ONE host-side barrier across the ranks is required between fms_als_planes_open_peers and the first
+ * half-step. */
+FMS_API int fms_als_planes_flag_sync(fms_ctx *ctx, int enable);
 /* number of replicas currently mapped for a side (0 = none): lets a host skip the handle exchange when the mappings of
  * an earlier fit are still valid (same plane buffers, same world size) */
 FMS_API int fms_als_planes_peer_count(fms_ctx *ctx, int which, int *n_peers);
