@@ -246,11 +246,11 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
     const int32_t *__restrict__ stage_ptr, const int32_t *__restrict__ colp, const float *__restrict__ valp,
     const int32_t *__restrict__ cta_rows, float *__restrict__ T, __half *__restrict__ T_pl, float lambda,
     int64_t row_begin, int *__restrict__ info, float *__restrict__ dump, __half *const *__restrict__ peers, int n_peers,
-    const __half *__restrict__ S_pl, int dbg, FlagSync fs) {
+    const __half *__restrict__ S_pl, int dbg, FlagSync fs, int n_act) {
     using SM = Smem2<NSTG_, NSA, KS>;
     constexpr int V2_W_MMA = V2_W_SOLVE0 + NSW, V2_W_PROD0 = V2_W_MMA + 1;
     constexpr int V2_REGS_EPI = NSW > 12 ? 56 : 72, V2_REGS_SOLVE = NSW > 12 ? 96 : 104;
-    static_assert(NSW % 4 == 0 && V2_W_PROD0 + NP <= V2_WARPS && NSA <= NSW, "warp roles");
+    static_assert(NSW % 4 == 0 && V2_W_PROD0 + NP <= V2_WARPS, "warp roles");
     static_assert((N_EPI * V2_REGS_EPI + NSW * V2_REGS_SOLVE + (V2_WARPS - N_EPI - NSW) * V2_REGS_AUX) <= V2_WARPS * 80, "register budgets");
     // Parity waits tell adjacent phases apart only: a producer may run at most one ring revolution ahead of the issuer.  Its
     // previous stage was NP stages back and legitimately within NSTG_ of the issuer, so NSTG_ >= NP keeps it inside two
@@ -462,14 +462,17 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(V2_REGS_SOLVE));
         // ================================================================== solvers: one system per warp on the HMMA path
+        // n_act of the NSW solver warps take systems round robin (system `job` sits in buffer job % NSA).  Measured on cfg1's short-row
+        // half-step (16 buffers): 16 / 15 / 14 / 13 active solvers -> 11.3 / 11.7 / 12.3 / 13.1 ms, and 17 or 18 buffers for 16
+        // solvers (shallower ring) change nothing: the solvers, not the refill of their buffers, pace this half-step.
         const int sv = warp - V2_W_SOLVE0;
-        if (sv < NSA) {
-            float *S = reinterpret_cast<float *>(sm + SM::bufs) + (size_t)sv * V2_BUF_FLOATS;
-            float *bz = S + TL4::FLOATS, *invd = bz + D, *xs = invd + D;
-            uint32_t use = 0;
-            for (int64_t row = first + sv; row < last; row += NSA) {
-                mbar_wait(bar_g_full(sv), use & 1);
-                ++use;
+        if (sv < n_act) {
+            for (uint32_t job = (uint32_t)sv; first + job < last; job += (uint32_t)n_act) {
+                const int64_t row = first + job;
+                const int gb = (int)(job % NSA);
+                float *S = reinterpret_cast<float *>(sm + SM::bufs) + (size_t)gb * V2_BUF_FLOATS;
+                float *bz = S + TL4::FLOATS, *invd = bz + D, *xs = invd + D;
+                mbar_wait(bar_g_full(gb), (job / NSA) & 1);
                 if (DUMP) {
                     float *o = dump + (int64_t)(row - row_begin) * (D * D + D);
                     for (int c = 0; c < D; ++c) {
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
                 __syncwarp();
                 const uint2 prow = reinterpret_cast<const uint2 *>(stg)[lane];
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_g_empty(sv));          // tiles / scratch no longer needed
+                if (lane == 0) mbar_arrive(bar_g_empty(gb));          // tiles / scratch no longer needed
                 T[row * D + lane] = b0;
                 T[row * D + lane + 32] = b1;
                 const int64_t poff = row * PLANE_PITCH + 4 * lane;
@@ -708,6 +711,7 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
         // ring slots of KS x 16 ratings (one producer / issuer handshake per slot), ring depth and active solver warps per
         // row-length regime: many short systems -> 16 ratings per slot, 7 slots, 3 producers, 16 solver warps; few long ones ->
         // 4 x 16 ratings per slot, 6 slots (144 KB of gathers in flight, 6 of the 7 producer warps active), 6 solver warps
+        static const int nact_env = getenv("FMS_TC_NACT") ? atoi(getenv("FMS_TC_NACT")) : 0;   // experiments: active solver warps
         static const int dbg = getenv("FMS_TC_DBG") ? atoi(getenv("FMS_TC_DBG")) : 0;   // timing experiments (wrong results): see the kernel
         // in-kernel cross-rank ordering (flag words in the spare rows of the plane buffers), only with mapped replicas of BOTH sides
         tc::FlagSync fs = {nullptr, nullptr, 0, 0, 0, 0, 0};
@@ -732,7 +736,7 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
         FMS_CUDA(ctx, cudaFuncSetAttribute(tc::k_als_rows_tc64<DUMPF, LDG, NS, NA, KSV, NPV, NSWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         tc::k_als_rows_tc64<DUMPF, LDG, NS, NA, KSV, NPV, NSWV><<<grid, tc::V2_WARPS * 32, smem, ctx->stream>>>(                    \
             m_pl, A.ptr[which].p, A.stage_ptr[which].p, A.colp[which].p, A.valp[which].p, A.cta_rows[which].p, A.fac[which].p, t_hi,  \
-            lambda, rb, A.info.p, DUMP_PTR, peers, n_peers, p_hi, dbg, fs);                                                          \
+            lambda, rb, A.info.p, DUMP_PTR, peers, n_peers, p_hi, dbg, fs, nact_env > 0 && nact_env <= NA && nact_env <= NSWV ? nact_env : (NA < NSWV ? NA : NSWV));                                                          \
     } while (0)
         //                                  DUMP   LDGSTS slots bufs KS NP NSW
         if (dump && short_rows) FMS_TC2_LAUNCH(true, false, 7, 16, 1, 3, 16, dump);

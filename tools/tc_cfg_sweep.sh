@@ -1,0 +1,7 @@
+#!/bin/bash
+# users / items half-step time for active-solver counts and ring/buffer configurations (FMS_TC_NACT, FMS_TC_CFG)
+for spec in "$@"; do
+  nact=${spec##*:}
+  FMS_TC_NACT=$nact timeout 200 python bench.py --skip-svm --skip-cpu --skip-e2e --parity-rows 256 --steps 5 2>/dev/null \
+    | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('cfg $cfg nact $nact', d['roofline']['iteration'], 'parity', d['parity']['max_rel'] if d.get('parity') else None)"
+done
