@@ -162,6 +162,7 @@ static int launch_generic(fms_ctx *ctx, int which, float lambda, int64_t rb, int
 
 int als_launch_half_step_generic(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t re) {
     const int d = ctx->als.rank;
+    if (als_wide_supported(ctx, d)) return als_launch_half_step_wide(ctx, which, lambda, rb, re);
     if (d <= 16) return launch_generic<1>(ctx, which, lambda, rb, re);
     if (d <= 32) return launch_generic<2>(ctx, which, lambda, rb, re);
     if (d <= 64) return launch_generic<4>(ctx, which, lambda, rb, re);

@@ -255,6 +255,8 @@ int als_build_csr(fms_ctx *ctx, const int64_t *h_user, const int64_t *h_item, co
 int als_launch_init(fms_ctx *ctx, int64_t seed);
 int als_launch_half_step_generic(fms_ctx *ctx, int which, float lambda, int64_t row_begin, int64_t row_end);
 int als_tc_supported(const fms_ctx *ctx, int rank);
+int als_wide_supported(const fms_ctx *ctx, int rank);                  // 64 < rank <= 128: FFMA Gramians + HMMA solver (als_wide.cu)
+int als_launch_half_step_wide(fms_ctx *ctx, int which, float lambda, int64_t row_begin, int64_t row_end);
 int als_launch_half_step_tc(fms_ctx *ctx, int which, float lambda, int64_t row_begin, int64_t row_end);
 int als_sgd_step_device(fms_ctx *ctx, const int64_t *d_u, const int64_t *d_i, const double *d_r, int64_t n, double lr, double ureg,
                         double ireg, const double *d_umean, const double *d_imean, int apply, double *d_out_u, double *d_out_i);
