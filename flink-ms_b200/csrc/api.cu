@@ -357,7 +357,7 @@ static int als_fit_loaded(fms_ctx *ctx, int rank, int iterations, double lambda,
     int bad = 0;
     FMS_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->als.info.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
     FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (bad) fail(ctx, FMS_OK, "fms_als_fit: %d row(s) of the last half-step broke down (non-positive pivot, dposv info != 0)", bad);
+    if (bad) fail(ctx, FMS_OK, "fms_als_fit: %d row(s) of the last half-step broke down (non-positive pivot, dposv info != 0) or left the +-65504 range of the rank-64 kernel's fp16 gather planes (fms_als_set_kernel(FMS_ALS_KERNEL_GENERIC) has no such range)", bad);
     else ctx->err.clear();
     return FMS_OK;
 }

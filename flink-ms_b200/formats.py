@@ -148,8 +148,9 @@ class QueryableStateClient:
     ALS_MODEL keys: "<id>-U", "<id>-I", "MEAN-U", "MEAN-I" -> (key, "f1;f2;...")   (ALSKafkaConsumer.java:78-92, SGD.java:143-147)
     SVM_MODEL keys: "<featureId>" -> (key, "w")  or, for a range-partitioned model, "<bucket>" -> (key, "id:w;id:w")
     A missing key returns None (Optional.empty, QueryClientHelper.java:136-139); None arguments raise like the
-    reference's NullPointerException.  Values are served from host copies of the model (point lookups); batches go
-    through Context.als_predict / svm_predict on the device.
+    reference's NullPointerException.  With a Context attached, ALS point lookups read the live device model (one row D2H), so
+    they see OnlineSGD updates; without one they are served from the host copy.  Batches go through Context.als_predict /
+    svm_predict on the device.  Ids unknown to the model stay unknown (the reference's Kafka consumer would insert them).
     """
 
     def __init__(self, ctx=None):
@@ -195,7 +196,12 @@ class QueryableStateClient:
             pos = int(np.searchsorted(ids, k))
             if pos >= len(ids) or ids[pos] != k:
                 return None
-            return key, ";".join(java_double_to_string(x) for x in F[pos])
+            row = F[pos]
+            if self._ctx is not None:
+                # the device model is the state: OnlineSGD.step(apply=True) updates it in place (SGD.java:204-217 writes the
+                # new factors back into the same queryable state), a host copy taken at load time would go stale
+                row = self._ctx.als_get_factor_rows(0 if kind == "U" else 1, pos, pos + 1)[1][0]
+            return key, ";".join(java_double_to_string(x) for x in row)
         if name == "SVM_MODEL":
             if self._svm is None:
                 return None

@@ -380,3 +380,20 @@ def test_online_sgd_operator_emits_reference_records(fms, ctx):
     assert recs[0].startswith("1,U,") and recs[1].startswith("11,I,")
     with pytest.raises(RuntimeError):
         fms.OnlineSGD(ctx, {}).step([(1, 11, 4.0)])
+
+
+def test_query_state_sees_online_sgd_updates(fms, ctx):
+    """SGD.java:204-217 writes the updated factors back into the queryable state: a point lookup after an applied batch must
+    return the NEW row (the client reads the device model, not the host copy it was loaded from)."""
+    formats = __import__("importlib").import_module("flink-ms_b200.formats")
+    uid = np.array([1, 2], np.int64); iid = np.array([10, 11], np.int64)
+    U = np.array([[0.5, -1.25], [2.0, 0.125]]); I = np.array([[1.0, 3.0], [-0.75, 0.2]])
+    client = formats.QueryableStateClient(ctx)
+    client.load_als(uid, U, iid, I)
+    before = client.queryState("ALS_MODEL", "1-U")
+    assert before == ("1-U", "0.5;-1.25")
+    recs = fms.OnlineSGD(ctx, {"learningRate": "0.1"}).step([(1, 11, 4.0)], apply=True)
+    after = client.queryState("ALS_MODEL", "1-U")
+    assert after != before
+    assert recs[0] == "1,U," + after[1]                     # the record the operator emitted is what the state now holds
+    assert client.queryState("ALS_MODEL", "2-U") == ("2-U", "2.0;0.125")      # untouched row
