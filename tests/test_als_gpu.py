@@ -392,7 +392,7 @@ def test_query_state_sees_online_sgd_updates(fms, ctx):
     client.load_als(uid, U, iid, I)
     before = client.queryState("ALS_MODEL", "1-U")
     assert before == ("1-U", "0.5;-1.25")
-    recs = fms.OnlineSGD(ctx, {"learningRate": "0.1"}).step([(1, 11, 4.0)], apply=True)
+    recs = fms.OnlineSGD(ctx, {"learningRate": "0.1", "userMean": "0.1;0.2", "itemMean": "0.3;0.4"}).step([(1, 11, 4.0)], apply=True)
     after = client.queryState("ALS_MODEL", "1-U")
     assert after != before
     assert recs[0] == "1,U," + after[1]                     # the record the operator emitted is what the state now holds

@@ -15,6 +15,11 @@ WANT = {
     "sm__pipe_tensor_subunit_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct",
     "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active": "tc_pipe_pct",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor_cycles_pct",
+    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active": "hmma_issue_pct",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "smem_lsu_wavefronts_pct",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "smem_tc_wavefronts_pct",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
     "launch__registers_per_thread": "regs",
