@@ -345,6 +345,7 @@ def main():
     ap.add_argument("--als-chunks", type=int, default=1, help="N>1, without --als-p2p 1: solve each shard in this many chunks, all-gather overlapped")
     ap.add_argument("--als-p2p", type=int, default=1, help="N>1: the kernel stores plane rows into all replicas over NVLink (CUDA IPC)")
     ap.add_argument("--svm-kernel", type=int, default=0)
+    ap.add_argument("--svm-p2p", type=int, default=1, help="N>1: fused push / flag / sum / apply kernel over IPC-mapped buffers instead of NCCL")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: --warmup < 3 violates the timing rules; using 3")
@@ -526,24 +527,32 @@ def main():
 
     # ---------------------------------------------------------------------------------------- predict (configs[4])
     predict = None
-    if rank == 0 and world == 1:
+    if True:
+        # every rank holds a full replica of the model after finalize(): the queries are sharded round-robin over the ranks
+        # ("predict: replicas, shard queries"), time = max over ranks, value = all queries / that time
+        D.DistributedALS(D.ContextALSBackend(ctx, dev), d).refresh_replicas()       # the e2e leg skipped the final all-gather
         rng = np.random.default_rng(7)
-        nq = 1_000_000
+        nq_total = 1_000_000
+        all_u = rng.integers(0, args.users, nq_total, dtype=np.int64)
+        all_i = rng.integers(0, args.items, nq_total, dtype=np.int64)
+        nq = len(all_u[rank::world])
         # query and result buffers in pinned host memory (a JVM host's direct ByteBuffers)
         qu = torch.empty(nq, dtype=torch.int64, pin_memory=True).numpy()
         qi = torch.empty(nq, dtype=torch.int64, pin_memory=True).numpy()
-        qu[:] = rng.integers(0, args.users, nq, dtype=np.int64)
-        qi[:] = rng.integers(0, args.items, nq, dtype=np.int64)
+        qu[:] = all_u[rank::world]
+        qi[:] = all_i[rank::world]
         p_out = torch.empty(nq, dtype=torch.float64, pin_memory=True).numpy()
         p_found = torch.empty(nq, dtype=torch.uint8, pin_memory=True).numpy()
         ctx.als_predict(qu, qi, p_out, p_found)                                      # warm-up (fp64 model copy, scratch)
+        barrier()
         t0 = time.perf_counter()
         for _ in range(5):
             out, found = ctx.als_predict(qu, qi, p_out, p_found)
-        dtp = (time.perf_counter() - t0) / 5
-        predict = {"metric": "als_lookups_per_sec", "value": nq / dtp, "unit": "lookups/s", "batch": nq,
-                   "found_fraction": float(found.mean()),
-                   "note": "fms_als_predict through the C-ABI: pinned host ids in, H2D, id lookup + fp64 dot on device, D2H into pinned host buffers"}
+        dtp = max_over_ranks((time.perf_counter() - t0) / 5)
+        predict = {"metric": "als_lookups_per_sec", "value": nq_total / dtp, "unit": "lookups/s", "batch": nq_total,
+                   "found_fraction": float(found.mean()), "replicas": world,
+                   "note": "fms_als_predict through the C-ABI: pinned host ids in, H2D, id lookup + fp64 dot on device, D2H into pinned "
+                           "host buffers; one model replica per rank, queries sharded round-robin, max over ranks"}
 
     # ---------------------------------------------------------------------------------------- CPU baseline (rank 0, N=1)
     cpu = None
@@ -591,7 +600,9 @@ def bench_svm(args, fms, D, synth, dev, rank, world, local_rank, peak, peak_src,
     ctx.svm_set_kernel(args.svm_kernel)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     ctx.svm_load(None, y_host, bid, K, rank, world, 1.0, 1.0, 42, dim=dim, device_ptr=X.data_ptr())
-    dsvm = D.DistributedSVM(D.ContextSVMBackend(ctx, dev))
+    svm_backend = D.ContextSVMBackend(ctx, dev)
+    svm_p2p = bool(world > 1 and args.svm_p2p and svm_backend.enable_p2p())
+    dsvm = D.DistributedSVM(svm_backend)
     rounds, warm = args.svm_rounds, 3
     for _ in range(warm):
         dsvm.round(-1)
@@ -616,7 +627,9 @@ def bench_svm(args, fms, D, synth, dev, rank, world, local_rank, peak, peak_src,
            "config": {"workload": f"CoCoA/SDCA linear SVM, {n} x {dim} dense fp32 synthetic (BASELINE.json configs[3]); "
                                   f"K={K} blocks for every N (block_id = i mod K, n_k = {n // K}), H = n_k (one epoch per round), "
                                   f"lambda=1 stepsize=1 seed=42",
-                      "parallelism": "1 GPU" if world == 1 else f"blocks k = g mod {world} on GPU g; delta-w all-reduced per round",
+                      "parallelism": "1 GPU" if world == 1 else (f"blocks k = g mod {world} on GPU g; " + (
+                          "delta-w pushed into every rank's exchange buffer over NVLink (CUDA IPC), epoch flags, rank-ordered sum + apply "
+                          "in ONE kernel per round -- no collective call" if svm_p2p else "delta-w all-reduced per round (NCCL)")),
                       "l2": "X is 41 GB, far larger than L2"},
            "roofline": {"bound": "hbm", "kernel": "SVM block sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak,

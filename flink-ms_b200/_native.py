@@ -57,6 +57,10 @@ SIGNATURES = {
     "fms_als_planes_updated": (C.c_int, [_vp, C.c_int]),
     "fms_als_planes_peer_count": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)]),
     "fms_als_planes_flag_sync": (C.c_int, [_vp, C.c_int]),
+    "fms_svm_exchange_ipc_handle": (C.c_int, [_vp, C.c_int, _vp]),
+    "fms_svm_exchange_open_peers": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "fms_svm_round_exchange": (C.c_int, [_vp, C.c_int64]),
+    "fms_svm_exchange_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "fms_als_last_info": (C.c_int, [_vp, _i64p]),
     "fms_als_set_kernel": (C.c_int, [_vp, C.c_int]),
     "fms_svm_fit": (C.c_int, [_vp, _vp, C.c_int, _i64p, _i32p, _f64p, C.c_int64, C.c_int32, _i32p, C.c_int, C.c_int,
@@ -257,6 +261,22 @@ class Context:
 
     def als_planes_open_peers(self, which, handles: bytes, n: int):
         self._check(self._lib.fms_als_planes_open_peers(self._h, which, C.c_char_p(handles) if n else None, n))
+
+    def svm_exchange_ipc_handle(self, n_ranks: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.fms_svm_exchange_ipc_handle(self._h, n_ranks, buf))
+        return buf.raw
+
+    def svm_exchange_open_peers(self, handles: bytes, n_ranks: int, my_rank: int):
+        assert len(handles) == 64 * n_ranks
+        self._check(self._lib.fms_svm_exchange_open_peers(self._h, C.create_string_buffer(handles, len(handles)), n_ranks, my_rank))
+
+    def svm_round_exchange(self, local_iterations: int = -1):
+        self._check(self._lib.fms_svm_round_exchange(self._h, local_iterations))
+
+    def svm_exchange_status(self):
+        t = C.c_int(0)
+        self._check(self._lib.fms_svm_exchange_status(self._h, C.byref(t)))
 
     def als_planes_flag_sync(self, enable: bool):
         self._check(self._lib.fms_als_planes_flag_sync(self._h, 1 if enable else 0))

@@ -691,6 +691,40 @@ FMS_API int fms_svm_apply_delta(fms_ctx *ctx) {
     return svm_launch_apply(ctx);
 }
 
+FMS_API int fms_svm_exchange_ipc_handle(fms_ctx *ctx, int n_ranks, void *handle64) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_exchange_ipc_handle");
+    CHECK_CTX(ctx);
+    return svm_exchange_handle(ctx, n_ranks, handle64);
+}
+
+FMS_API int fms_svm_exchange_open_peers(fms_ctx *ctx, const void *handles, int n_ranks, int my_rank) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_exchange_open_peers");
+    CHECK_CTX(ctx);
+    return svm_exchange_open(ctx, handles, n_ranks, my_rank);
+}
+
+FMS_API int fms_svm_round_exchange(fms_ctx *ctx, int64_t local_iterations) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_round_exchange");
+    CHECK_CTX(ctx);
+    if (!ctx->svm.loaded) return fail(ctx, FMS_ERR_STATE, "fms_svm_round_exchange: load first");
+    NvtxRange nvtx_("fms.svm.round_exchange");
+    FMS_TRY(svm_launch_sweep(ctx, local_iterations));
+    return svm_launch_exchange_apply(ctx);
+}
+
+FMS_API int fms_svm_exchange_status(fms_ctx *ctx, int *timed_out) {
+    GROUP_UNSUPPORTED(ctx, "fms_svm_exchange_status");
+    CHECK_CTX(ctx);
+    int v = 0;
+    if (ctx->svm.xchg_err.p) {
+        FMS_CUDA(ctx, cudaMemcpyAsync(&v, ctx->svm.xchg_err.p, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
+        FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (timed_out) *timed_out = v;
+    if (v) return fail(ctx, FMS_ERR_STATE, "fms_svm_round_exchange: a peer rank never published its epoch (flag wait timed out)");
+    return FMS_OK;
+}
+
 __global__ void k_widen(const float *__restrict__ in, int64_t n, double *__restrict__ out) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k < n) out[k] = (double)in[k];

@@ -247,6 +247,7 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
 #pragma unroll
     for (int q = 0; q < NQ; ++q) zq[q] = bz[lane + 32 * q];
     const int lp = (lane >> 3) * 128 + ((lane & 7) >> 1) * 4 + (lane & 1);      // lane part of Tiles::at(k, 32 q + lane)
+    const int sk = (lane >> 3) & 1, sk16 = 16 * sk;                             // row-order skew of the odd lane groups (bank conflicts)
 #pragma unroll
     for (int q = NQ - 1; q >= 0; --q) {
         float x = 0.f;
@@ -264,12 +265,14 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
             }
             if (rel >= 0 && rel < 8) x = xc;
             // columns left of the panel: z_i -= sum_c L[j0 + c][i] x_c
+            // rows j0 + c sit 16 floats apart, the four 8-column tiles of a lane group 128 floats: all four groups would hit the
+            // same 8 banks (4-way conflict).  Odd groups walk the rows in the order 1, 0, 3, 2, ...: two bank sets, 2 wavefronts.
             const float *p = S + (I * (I + 1)) * 128 + 2 * hh + 4 * q * 128 + lp;
             float acc = zq[q];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const float xv = __shfl_sync(0xffffffffu, xc, jr + c);
-                acc = fmaf(-p[16 * c], xv, acc);
+                const float xv = __shfl_sync(0xffffffffu, xc, jr + (c ^ sk));
+                acc = fmaf(-p[16 * c + ((c & 1) ? -sk16 : sk16)], xv, acc);
             }
             if (rel < 0) zq[q] = acc;
         }
@@ -287,7 +290,8 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
                     const int I = k >> 4;
                     const float *p = S + (I * (I + 1) + 4 * q2) * 128 + (k & 7) * 16 + ((k >> 3) & 1) * 2 + lp;
                     const float4 xv = *reinterpret_cast<const float4 *>(xs + k);
-                    acc = fmaf(-p[48], xv.w, fmaf(-p[32], xv.z, fmaf(-p[16], xv.y, fmaf(-p[0], xv.x, acc))));
+                    const float x0 = sk ? xv.y : xv.x, x1 = sk ? xv.x : xv.y, x2 = sk ? xv.w : xv.z, x3 = sk ? xv.z : xv.w;
+                    acc = fmaf(-p[48 - sk16], x3, fmaf(-p[32 + sk16], x2, fmaf(-p[16 - sk16], x1, fmaf(-p[sk16], x0, acc))));
                 }
                 zq[q2] = acc;
             }

@@ -127,6 +127,12 @@ struct SvmState {
     std::vector<int> local_blocks;           // block ids swept by this rank
     DevBuf<int32_t> d_local_blocks;
     DevBuf<unsigned long long> peer_delta;   // group ctx: device table of every member's delta buffer (fused all-reduce + apply)
+    // one process per GPU: exchange buffer [2 epoch parities][n ranks][dim] floats + 64 flag words, mapped into every rank (CUDA IPC)
+    DevBuf<float> xchg;
+    DevBuf<unsigned long long> xchg_tab;     // device table: every rank's exchange buffer
+    DevBuf<int> xchg_err;                    // set by a kernel whose flag wait timed out (a peer died)
+    void *xchg_open[64] = {};
+    int xchg_n = 0, xchg_rank = 0, xchg_epoch = 0, xchg_dim = 0;
 };
 
 }  // namespace fms
@@ -282,6 +288,10 @@ int group_svm_fit(fms_ctx *P, const void *X, int x_dtype, const int64_t *csr_ptr
 int svm_launch_sweep(fms_ctx *ctx, int64_t local_iterations);
 int svm_launch_reduce_delta(fms_ctx *ctx);
 int svm_launch_apply(fms_ctx *ctx);
+int svm_exchange_handle(fms_ctx *ctx, int n_ranks, void *handle64);
+int svm_exchange_open(fms_ctx *ctx, const void *handles, int n_ranks, int my_rank);
+void svm_exchange_close(fms_ctx *ctx);
+int svm_launch_exchange_apply(fms_ctx *ctx);
 int svm_predict_device(fms_ctx *ctx, const void *d_X, int x_kind, const int64_t *d_ptr, const int32_t *d_idx, int64_t n,
                        int32_t dim, const double *d_w, double threshold, int decision, double *d_out);
 

@@ -239,6 +239,121 @@ int svm_launch_apply(fms_ctx *ctx) {
     return FMS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ K6' exchange + apply, one process per GPU
+// The delta-w all-reduce and the apply step as ONE kernel per rank over IPC-mapped peer memory (what k_svm_allreduce_apply is
+// for the single-process group ctx): every rank pushes its dim floats into slot [epoch parity][rank] of EVERY rank's exchange
+// buffer (NVLink stores), publishes the epoch into flag word [rank] of every buffer (system-scope release), waits until all flag
+// words of its OWN buffer reached the epoch, sums the slots in rank order (identical on every rank) and applies the step.
+// Two parities suffice: a rank rewrites a slot two rounds later, after an apply that waited for flags every peer set only after
+// finishing its previous round's reads.
+__device__ __forceinline__ int ld_acquire_sys_i(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_i(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(1024) k_svm_exchange_apply(float *__restrict__ w, const float *__restrict__ delta, float *const *__restrict__ peers, int n,
+                                                             int me, int dim, int epoch, float scaling, int *__restrict__ err) {
+    const size_t slot = ((size_t)(epoch & 1) * n + me) * dim, flags_at = (size_t)2 * n * dim;
+    for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+        const float v = delta[j];
+        for (int p = 0; p < n; ++p) peers[p][slot + j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int p = 0; p < n; ++p) st_release_sys_i(reinterpret_cast<int *>(peers[p] + flags_at) + me, epoch);
+    }
+    if (threadIdx.x < n) {
+        const int *f = reinterpret_cast<const int *>(peers[me] + flags_at) + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys_i(f) < epoch) {
+            if (clock64() - t0 > 8000000000LL) { atomicExch(err, 1); break; }     // ~4 s: a peer is gone; do not hang the GPU
+        }
+    }
+    __syncthreads();
+    const float *mine = peers[me] + (size_t)(epoch & 1) * n * dim;
+    for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < n; ++r) s += __ldcv(mine + (size_t)r * dim + j);
+        w[j] = fmaf(s, scaling, w[j]);
+    }
+}
+
+static size_t xchg_floats(int n_ranks, int dim) { return (size_t)2 * n_ranks * dim + 64; }
+
+int svm_exchange_handle(fms_ctx *ctx, int n_ranks, void *handle64) {
+    SvmState &S = ctx->svm;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    if (!S.loaded) return fail(ctx, FMS_ERR_STATE, "fms_svm_exchange_ipc_handle: load first");
+    if (n_ranks < 2 || n_ranks > 64 || !handle64) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_exchange_ipc_handle: n_ranks %d", n_ranks);
+    svm_exchange_close(ctx);
+    S.xchg.release();                                            // a fresh allocation per geometry: handles name allocations
+    FMS_CUDA(ctx, S.xchg.alloc(xchg_floats(n_ranks, S.dim)));
+    FMS_CUDA(ctx, cudaMemsetAsync(S.xchg.p, 0, xchg_floats(n_ranks, S.dim) * sizeof(float), ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    S.xchg_dim = S.dim;
+    cudaIpcMemHandle_t h;
+    FMS_CUDA(ctx, cudaIpcGetMemHandle(&h, S.xchg.p));
+    memcpy(handle64, &h, sizeof h);
+    return FMS_OK;
+}
+
+void svm_exchange_close(fms_ctx *ctx) {
+    SvmState &S = ctx->svm;
+    for (int r = 0; r < S.xchg_n; ++r) {
+        if (S.xchg_open[r]) cudaIpcCloseMemHandle(S.xchg_open[r]);
+        S.xchg_open[r] = nullptr;
+    }
+    S.xchg_n = 0;
+    S.xchg_epoch = 0;
+}
+
+int svm_exchange_open(fms_ctx *ctx, const void *handles, int n_ranks, int my_rank) {
+    SvmState &S = ctx->svm;
+    if (!S.xchg.p || S.xchg_dim != S.dim) return fail(ctx, FMS_ERR_STATE, "fms_svm_exchange_open_peers: fms_svm_exchange_ipc_handle first");
+    if (n_ranks < 2 || n_ranks > 64 || my_rank < 0 || my_rank >= n_ranks || !handles) return fail(ctx, FMS_ERR_INVALID_ARG, "fms_svm_exchange_open_peers: rank %d of %d", my_rank, n_ranks);
+    svm_exchange_close(ctx);
+    unsigned long long tab[64];
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == my_rank) { tab[r] = (unsigned long long)(uintptr_t)S.xchg.p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)r, sizeof h);
+        void *pp = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&pp, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            S.xchg_n = r;
+            svm_exchange_close(ctx);
+            return fail(ctx, FMS_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        S.xchg_open[r] = pp;
+        tab[r] = (unsigned long long)(uintptr_t)pp;
+    }
+    S.xchg_n = n_ranks;
+    S.xchg_rank = my_rank;
+    S.xchg_epoch = 0;
+    FMS_CUDA(ctx, S.xchg_tab.alloc(64));
+    FMS_CUDA(ctx, S.xchg_err.alloc(1));
+    FMS_CUDA(ctx, cudaMemcpyAsync(S.xchg_tab.p, tab, sizeof(unsigned long long) * n_ranks, cudaMemcpyHostToDevice, ctx->stream));
+    FMS_CUDA(ctx, cudaMemsetAsync(S.xchg_err.p, 0, sizeof(int), ctx->stream));
+    // fresh flag words; the HOST must put one barrier across the ranks between this call and the first round
+    FMS_CUDA(ctx, cudaMemsetAsync(S.xchg.p + (size_t)2 * n_ranks * S.dim, 0, 64 * sizeof(int), ctx->stream));
+    FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FMS_OK;
+}
+
+int svm_launch_exchange_apply(fms_ctx *ctx) {
+    SvmState &S = ctx->svm;
+    if (S.xchg_n < 2) return fail(ctx, FMS_ERR_STATE, "fms_svm_round_exchange: fms_svm_exchange_open_peers first");
+    ++S.xchg_epoch;
+    k_svm_exchange_apply<<<1, 1024, 0, ctx->stream>>>(S.w.p, S.delta.p, reinterpret_cast<float *const *>(S.xchg_tab.p), S.xchg_n, S.xchg_rank, S.dim,
+                                                       S.xchg_epoch, (float)(S.stepsize / (double)S.blocks), S.xchg_err.p);
+    FMS_LAUNCH_CHECK(ctx);
+    S.w64_valid = false;
+    return FMS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ K7 predict
 // One warp per query row, fp64 accumulate.  d_X: dense fp32 / dense fp64 / CSR fp64 values.
 __global__ void k_svm_predict(const void *__restrict__ Xv, int x_kind, const int64_t *__restrict__ cptr,

@@ -179,6 +179,11 @@ class DistributedALS:
             self._gather(self.b.factor_tensor(which, self.rank_dim))
         self._stale.clear()
 
+    def refresh_replicas(self):
+        """All-gather both fp32 factor matrices unconditionally (after a fit that skipped finalize, before serving predict)."""
+        self._stale.update((0, 1))
+        self.finalize()
+
     def _token(self):
         if self._tok is None:
             self._tok = torch.zeros(1, device=self.b.device)
@@ -262,6 +267,25 @@ class ContextSVMBackend:
     def apply(self):
         self.ctx.svm_apply_delta()
 
+    p2p = False
+
+    def enable_p2p(self, group=None):
+        """Map every rank's delta-w exchange buffer into this process (CUDA IPC): a round is then the sweep plus ONE kernel
+        that pushes the rank's delta into all buffers over NVLink, waits for everybody's epoch flag and applies the rank-ordered
+        sum -- no collective call between rounds.  A failing IPC exchange raises."""
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = torch.frombuffer(bytearray(self.ctx.svm_exchange_ipc_handle(world)), dtype=torch.uint8).to(self.device)
+        table = torch.empty(world * 64, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(table, mine, group=group)
+        self.ctx.svm_exchange_open_peers(table.cpu().numpy().tobytes(), world, rank)
+        dist.all_reduce(torch.zeros(1, device=self.device), group=group)     # fresh flag words everywhere before the first round
+        torch.cuda.synchronize(self.device)
+        self.p2p = True
+        return True
+
+    def round_exchange(self, local_iterations):
+        self.ctx.svm_round_exchange(local_iterations)
+
 
 class DistributedSVM:
     """CoCoA outer round: local block sweeps -> all-reduce(sum) of the delta -> w += scaling * delta."""
@@ -272,6 +296,9 @@ class DistributedSVM:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 
     def round(self, local_iterations):
+        if self.world > 1 and getattr(self.b, "p2p", False):
+            self.b.round_exchange(local_iterations)          # sweep + fused push / flag wait / rank-ordered sum / apply
+            return
         self.b.sweep(local_iterations)
         if self.world > 1:
             delta = self.b.delta_tensor()

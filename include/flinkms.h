@@ -239,6 +239,16 @@ FMS_API int fms_svm_sweep(fms_ctx *ctx, int64_t local_iterations);
 FMS_API int fms_svm_delta_device(fms_ctx *ctx, void **dev_ptr, int32_t *dim);
 /* w += (stepsize / blocks) * delta */
 FMS_API int fms_svm_apply_delta(fms_ctx *ctx);
+/* One process per GPU WITHOUT a collective library between the rounds (what fms_als_planes_* is for ALS): every rank maps every
+ * rank's exchange buffer (CUDA IPC); fms_svm_round_exchange = fms_svm_sweep + ONE kernel that pushes the rank's delta-w into all
+ * buffers over NVLink, publishes an epoch flag, waits for every rank's flag, sums in rank order and applies the step -- the
+ * all-reduce and SVM.scala's `weights += scaling * sum` in one launch.  Protocol: every rank calls _ipc_handle(n_ranks), the host
+ * exchanges the 64-byte handles, every rank calls _open_peers with all n handles in rank order, then ONE host barrier, then the
+ * same number of fms_svm_round_exchange calls on every rank.  fms_svm_exchange_status reports a timed-out flag wait. */
+FMS_API int fms_svm_exchange_ipc_handle(fms_ctx *ctx, int n_ranks, void *handle64);
+FMS_API int fms_svm_exchange_open_peers(fms_ctx *ctx, const void *handles, int n_ranks, int my_rank);
+FMS_API int fms_svm_round_exchange(fms_ctx *ctx, int64_t local_iterations);
+FMS_API int fms_svm_exchange_status(fms_ctx *ctx, int *timed_out);
 FMS_API int fms_svm_set_kernel(fms_ctx *ctx, int kernel);
 
 /* ------------------------------------------------------------------------------------------------

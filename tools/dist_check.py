@@ -50,8 +50,23 @@ ws = ctx.svm_get_weights(dim)
 ref = fms.Context(lr)
 w1 = ref.svm_fit(X, y, bid, K, 4, -1, 1.0, 1.0, 42)
 err = np.abs(ws - w1).max() / np.abs(w1).max()
-print(f"[rank {rank}] SVM sharded vs single rel err {err:.3e}", flush=True)
+print(f"[rank {rank}] SVM sharded (NCCL all-reduce) vs single rel err {err:.3e}", flush=True)
 ok &= err < 1e-5
+# the same fit with the fused exchange kernel over IPC-mapped buffers; every rank must end with the SAME bits
+ctx2 = fms.Context(lr)
+ctx2.svm_load(X, y, bid, K, rank, world, 1.0, 1.0, 42)
+be = D.ContextSVMBackend(ctx2, dev)
+be.enable_p2p()
+D.DistributedSVM(be).fit(4, -1)
+ctx2.svm_exchange_status()
+wx = ctx2.svm_get_weights(dim)
+errx = np.abs(wx - w1).max() / np.abs(w1).max()
+wt = torch.from_numpy(wx).to(dev)
+lo, hi = wt.clone(), wt.clone()
+dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+same_bits = bool((lo == hi).all().item())
+print(f"[rank {rank}] SVM sharded (exchange kernel) vs single rel err {errx:.3e}; identical on all ranks: {same_bits}", flush=True)
+ok &= errx < 1e-5 and same_bits
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
