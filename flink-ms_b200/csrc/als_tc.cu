@@ -703,12 +703,14 @@ static int launch_tc(fms_ctx *ctx, int which, float lambda, int64_t rb, int64_t 
     const int n_peers = A.peer_n[which];
     const int64_t rows = re - rb;
     const int grid = (int)(rows < ctx->sm_count ? rows : ctx->sm_count);
-    // producer flavour: LDGSTS for short rows (see the kernel), TMA gather4 for long ones
+    // producer flavour per half-step (results are bitwise equal either way)
     const int64_t n_side = which == 0 ? A.n_users : A.n_items;
     const bool short_rows = n_side > 0 && A.nnz / n_side < 16 * tc::KROWS;
     static const int force_kernel = getenv("FMS_ALS_KERNEL") ? atoi(getenv("FMS_ALS_KERNEL")) : 0;     // experiments: 3 = TMA, 4 = LDGSTS producers
     const int kern = force_kernel ? force_kernel : A.kernel;
-    const bool ldgsts = !dump && (kern == FMS_ALS_KERNEL_TC_LDGSTS || (kern != FMS_ALS_KERNEL_TC_TMA && short_rows));
+    // round-2 A/B with the HMMA solver (profiles/README.md): TMA gather4 now wins for short rows (users 11.21 vs 11.31 ms: fewer
+    // producer instructions beside 16 busy solver warps), LDGSTS for long rows (items 4.07 vs 4.16 ms) -- the reverse of round 1
+    const bool ldgsts = !dump && (kern == FMS_ALS_KERNEL_TC_LDGSTS || (kern != FMS_ALS_KERNEL_TC_TMA && !short_rows));
     {
         // ring slots of KS x 16 ratings (one producer / issuer handshake per slot), ring depth and active solver warps per
         // row-length regime: many short systems -> 16 ratings per slot, 7 slots, 3 producers, 16 solver warps; few long ones ->

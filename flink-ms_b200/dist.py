@@ -1,17 +1,19 @@
 """One-process-per-GPU sharding of the two hot paths over torch.distributed (NCCL on GPUs, gloo in CPU tests).
 
-ALS: every rank holds the full CSR pair and full factor replicas, solves the row shard
-[g*S, (g+1)*S) of the side being updated, then the shards are ALL-GATHERED into every replica -- the exchange
-Flink does with a join + coGroup network shuffle between half-steps (Appendix A.1 `updateFactors` message
-build).  Per-row arithmetic is identical to the 1-GPU run, so results are bitwise equal.  On GPUs the shard is
-solved in up to `max_chunks` chunks (default 1: measured slower than the plain all-gather at 2 GPUs because the persistent
-solver kernel owns every SM, so the NCCL kernel cannot really run beside it) with chunk k's all-gather on a second stream;
-or -- `ContextALSBackend.enable_p2p` -- the kernel itself stores each solved row into every rank's replica over NVLink
-(CUDA IPC mappings), and only a barrier follows the half-step.
+ALS: every rank holds the CSR rows of its own shard and full factor replicas, solves the row shard
+[g*S, (g+1)*S) of the side being updated, then every replica gets the solved shard -- the exchange Flink does with a
+join + coGroup network shuffle between half-steps (Appendix A.1 `updateFactors` message build).  Per-row arithmetic is
+identical to the 1-GPU run, so results are bitwise equal.  How the shard travels:
+  * `ContextALSBackend.enable_p2p` (rank 64): the kernel itself stores each solved plane row into every rank's replica over
+    NVLink (CUDA IPC mappings) and the half-step kernels order themselves with epoch flags kept in the replicas -- no
+    collective and no host barrier between half-steps;
+  * otherwise an NCCL all-gather of the solved shard (optionally in `max_chunks` chunks on a second stream; default 1: the
+    persistent solver kernel owns every SM, so the NCCL kernel cannot really run beside it).
 
-SVM: rank g sweeps the CoCoA blocks k with k % G == g; the per-rank sum of block deltas (dim floats) is
-ALL-REDUCED and every rank applies w += (stepsize / blocks) * delta -- FlinkML's broadcast of w and
-union+reduce of the K delta vectors (Appendix A.2).
+SVM: rank g sweeps the CoCoA blocks k with k % G == g; the per-rank sum of block deltas (dim floats) is summed over the ranks
+and every rank applies w += (stepsize / blocks) * delta -- FlinkML's broadcast of w and union+reduce of the K delta vectors
+(Appendix A.2) -- either by ONE fused kernel over IPC-mapped exchange buffers (`ContextSVMBackend.enable_p2p`) or by an NCCL
+all-reduce followed by the apply kernel.
 
 The compute backend is any object with the small interface used below; the product backend is
 `_native.Context` (CUDA kernels through the C-ABI).  torch is plumbing only: device views + collectives.
@@ -181,6 +183,8 @@ class DistributedALS:
 
     def refresh_replicas(self):
         """All-gather both fp32 factor matrices unconditionally (after a fit that skipped finalize, before serving predict)."""
+        if self.world == 1:
+            return
         self._stale.update((0, 1))
         self.finalize()
 
