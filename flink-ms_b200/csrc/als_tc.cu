@@ -218,6 +218,7 @@ struct Smem2 {
     static constexpr int bars = bufs + NSA * V2_BUF_FLOATS * 4;
     static constexpr int n_bars = 2 * NSTG_ + 2 * NACC + 2 * NSA;
     static constexpr int tmem_ptr = bars + n_bars * 8;
+    static constexpr int scale = tmem_ptr + 8;                 // two floats: power-of-two scale of the system being unpacked
     static constexpr int total = tmem_ptr + 16;
 };
 
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
     auto bar_g_full = [&](int g) { return bar0 + 8u * (2 * NSTG_ + 2 * NACC + g); };
     auto bar_g_empty = [&](int g) { return bar0 + 8u * (2 * NSTG_ + 2 * NACC + NSA + g); };
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sm + SM::tmem_ptr);
+    volatile float *scale_slot = reinterpret_cast<volatile float *>(sm + SM::scale);
 
     // zero the ring once: the R / R' chunks only ever get their first four bytes per row rewritten
     for (int i = threadIdx.x; i < NSTG_ * STG / 16; i += blockDim.x) reinterpret_cast<uint4 *>(sm + SM::ring)[i] = make_uint4(0, 0, 0, 0);
@@ -422,6 +424,24 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
             mbar_wait(bar_acc_full(acc), (job / NACC) & 1);
             tc_fence_after();
             mbar_wait(bar_g_empty(g), ((job / NSA) & 1) ^ 1);
+            // fp16-packed solver (cm::solve_tiles_h): the system goes out scaled by the power of two that brings its first diagonal
+            // entry into [1, 2) -- matrix and right-hand side alike, so x is unchanged.  Warp 0 owns that entry; one named barrier
+            // among the four epilogue warps per system hands the factor over (two slots: a slow warp still reads the previous one).
+            float sc = 1.f;
+            if (FMS_CHOL_F16 && !DUMP) {
+                if (q == 0) {
+                    float e1[4], e2[4];
+                    tc_ld16x256_x1(tmem_base + (uint32_t)acc * ACC_COLS, e1);
+                    tc_ld16x256_x1(tmem_base + (uint32_t)acc * ACC_COLS + 64, e2);
+                    tc_wait_ld();
+                    if (lane == 0) {
+                        const uint32_t ex = (__float_as_uint(fmaf(LO_INV, e2[0], e1[0]) + reg) >> 23) & 0x1ffu;      // sign + exponent
+                        scale_slot[job & 1] = (ex >= 1u && ex <= 253u) ? __uint_as_float((254u - ex) << 23) : 1.f;   // positive, normal
+                    }
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                sc = scale_slot[job & 1];
+            }
             float *buf = reinterpret_cast<float *>(sm + SM::bufs) + (size_t)g * V2_BUF_FLOATS;
             float4 *tiles = reinterpret_cast<float4 *>(buf) + (q * (q + 1)) * 32 + lane;       // tile (q, j) at + 32 j
             const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * ACC_COLS;
@@ -443,6 +463,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
                         v.w = fmaf(-LO_INV, d2[4 * jj + 3], -d1[4 * jj + 3]);
                         if (j == 2 * q) { v.x -= dg0 ? reg : 0.f; v.y -= dg1 ? reg : 0.f; }          // rows g   x cols 16 q + 2 t (+1)
                         if (j == 2 * q + 1) { v.z -= dg0 ? reg : 0.f; v.w -= dg1 ? reg : 0.f; }      // rows g+8 x cols 16 q + 8 + 2 t (+1)
+                        if (FMS_CHOL_F16 && !DUMP) { v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
                         tiles[32 * j] = v;
                     }
                 }
@@ -452,8 +473,8 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
             tc_wait_ld();
             if (t4 == 0) {
                 float *bz = buf + TL4::FLOATS;
-                bz[16 * q + g8] = -fmaf(bb[1], LO_INV, bb[0]);
-                bz[16 * q + g8 + 8] = -fmaf(bb[3], LO_INV, bb[2]);
+                bz[16 * q + g8] = -fmaf(bb[1], LO_INV, bb[0]) * sc;
+                bz[16 * q + g8 + 8] = -fmaf(bb[3], LO_INV, bb[2]) * sc;
             }
             tc_fence_before();
             __syncwarp();
@@ -484,7 +505,10 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
                     __syncwarp();
                 }
                 float x[2] = {0.f, 0.f};
-                if (!(dbg & 16)) cm::solve_tiles<4>(S, bz, invd, xs, lane, x);
+                if (!(dbg & 16)) {
+                    if (FMS_CHOL_F16 && !DUMP) cm::solve_tiles_h<4>(S, bz, invd, xs, lane, x);
+                    else cm::solve_tiles<4>(S, bz, invd, xs, lane, x);
+                }
                 const float b0 = x[0], b1 = x[1];
                 __half h0, l0, h1, l1;
                 split_half(b0, h0, l0);

@@ -10,7 +10,7 @@
 
 using namespace fms::cm;
 
-template <int MT>
+template <int MT, bool H>
 __global__ void __launch_bounds__(512, 1) k_solve(const float *__restrict__ A, const float *__restrict__ b, int n_sys, int reps, float *__restrict__ X,
                                                   long long *cyc) {
     using TL = Tiles<MT>;
@@ -26,18 +26,21 @@ __global__ void __launch_bounds__(512, 1) k_solve(const float *__restrict__ A, c
         {
             const int s = ((blockIdx.x * nw + warp) * reps + rep) % n_sys;
             const float *As = A + (size_t)s * D * D;
+            // fp16-packed variant: the caller scales the system by a power of two taken from the first diagonal entry
+            const float sc = H ? __uint_as_float((254u - ((__float_as_uint(As[0]) >> 23) & 0xffu)) << 23) : 1.f;
             // what the epilogue warps do in the real kernel: negated system in tile layout, -b
 #pragma unroll 1
             for (int I = 0; I < MT; ++I)
                 for (int j = 0; j <= 2 * I + 1; ++j) {
                     const float2 r0 = *reinterpret_cast<const float2 *>(As + (16 * I + g) * D + 8 * j + 2 * t);
                     const float2 r1 = *reinterpret_cast<const float2 *>(As + (16 * I + g + 8) * D + 8 * j + 2 * t);
-                    reinterpret_cast<float4 *>(S)[(I * (I + 1) + j) * 32 + lane] = make_float4(-r0.x, -r0.y, -r1.x, -r1.y);
+                    reinterpret_cast<float4 *>(S)[(I * (I + 1) + j) * 32 + lane] = make_float4(-r0.x * sc, -r0.y * sc, -r1.x * sc, -r1.y * sc);
                 }
-            for (int q = 0; q < D / 32; ++q) bz[lane + 32 * q] = -b[(size_t)s * D + lane + 32 * q];
+            for (int q = 0; q < D / 32; ++q) bz[lane + 32 * q] = -b[(size_t)s * D + lane + 32 * q] * sc;
             __syncwarp();
             float x[MT / 2];
-            solve_tiles<MT>(S, bz, invd, xs, lane, x);
+            if (H) solve_tiles_h<MT>(S, bz, invd, xs, lane, x);
+            else solve_tiles<MT>(S, bz, invd, xs, lane, x);
             for (int q = 0; q < MT / 2; ++q) X[(size_t)s * D + lane + 32 * q] = x[q];
             __syncwarp();
         }
@@ -61,7 +64,7 @@ static void chol_solve64(std::vector<double> &a, std::vector<double> &b, int d) 
     for (int i = d - 1; i >= 0; --i) { double v = b[i]; for (int k = i + 1; k < d; ++k) v -= a[k * d + i] * b[k]; b[i] = v / a[i * d + i]; }
 }
 
-template <int MT>
+template <int MT, bool H>
 static int run(int only_warps) {
     constexpr int D = 16 * MT;
     const int n_sys = 2048;
@@ -98,15 +101,15 @@ static int run(int only_warps) {
     for (int warps : {4, 8, 12, 16}) {
         const size_t smem = per_warp * warps;
         if (smem > 227 * 1024 || (only_warps && warps != only_warps)) continue;
-        cudaFuncSetAttribute(k_solve<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_solve<MT, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int reps = 16;
-        k_solve<MT><<<148, warps * 32, smem>>>(dA, db, n_sys, 1, dX, dc);
+        k_solve<MT, H><<<148, warps * 32, smem>>>(dA, db, n_sys, 1, dX, dc);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        k_solve<MT><<<148, warps * 32, smem>>>(dA, db, n_sys, reps, dX, dc);
+        k_solve<MT, H><<<148, warps * 32, smem>>>(dA, db, n_sys, reps, dX, dc);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0.f;
@@ -143,9 +146,11 @@ static int run(int only_warps) {
 int main(int argc, char **argv) {
     const int mt = argc > 1 ? atoi(argv[1]) : 4;
     const int only = argc > 2 ? atoi(argv[2]) : 0;
-    if (mt == 4) return run<4>(only);
-    if (mt == 8) return run<8>(only);
-    if (mt == 2) return run<2>(only);
+    const bool h = argc > 3 && argv[3][0] == 'h';               // fp16-packed products (solve_tiles_h)
+    if (h) printf("fp16-packed variant\n");
+    if (mt == 4) return h ? run<4, true>(only) : run<4, false>(only);
+    if (mt == 8) return h ? run<8, true>(only) : run<8, false>(only);
+    if (mt == 2) return h ? run<2, true>(only) : run<2, false>(only);
     printf("MT must be 2, 4 or 8\n");
     return 1;
 }
