@@ -9,7 +9,7 @@
 //   * a producer warp streams partner rows, 16 ratings per stage, through a 4-deep cp.async ring (mbarrier full / empty);
 //   * warps 0..3 (128 threads for the 136 8 x 8 blocks of the lower block triangle) accumulate G = sum y y^T and
 //     b = sum r y, then write -(G + lambda n I) in the fragment-tile layout and -b into one of NBUF system buffers;
-//   * NSOLVE solver warps each solve one buffered system at a time (3xTF32 HMMA blocked Cholesky) and store the fp32 row.
+//   * NSOLVE solver warps each solve one buffered system at a time (HMMA blocked Cholesky, fp16-packed products on a power-of-two scaled system) and store the fp32 row.
 // Reference: the per-row normal equations of FlinkML ALS.updateFactors (oracle/flinkml_oracle.c:als_half_step cites the Scala).
 #include "chol_mma.cuh"
 #include "common.cuh"
@@ -25,7 +25,7 @@ using TL = cm::Tiles<MT>;
 constexpr int BUF_FLOATS = TL::FLOATS + 3 * DP;                              // tiles | bz | scratch | xs
 constexpr int STAGE_FLOATS = CH * DP + CH;                                   // CH partner rows | CH ratings
 constexpr int N_BARS = 2 * NST + 2 * NBUF;
-constexpr size_t SMEM_BYTES = (size_t)(NST * STAGE_FLOATS + NBUF * BUF_FLOATS) * 4 + N_BARS * 8 + 16;
+constexpr size_t SMEM_BYTES = (size_t)(NST * STAGE_FLOATS + NBUF * BUF_FLOATS) * 4 + N_BARS * 8 + 16;     // + scale slots
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_als_rows_wide(const int64_t *__r
     float *stage = smem;                                     // NST x (CH x DP | CH)
     float *bufs = stage + NST * STAGE_FLOATS;                // NBUF x BUF_FLOATS
     const uint32_t bar0 = smem_u32(bufs + NBUF * BUF_FLOATS);
+    volatile float *scale_slot = bufs + NBUF * BUF_FLOATS + 2 * N_BARS;      // two floats behind the barriers
     auto st_full = [&](int s) { return bar0 + 8u * s; };
     auto st_empty = [&](int s) { return bar0 + 8u * (NST + s); };
     auto bar_full = [&](int b) { return bar0 + 8u * (2 * NST + b); };
@@ -169,15 +170,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_als_rows_wide(const int64_t *__r
             mbar_wait(bar_empty(bf), (uint32_t)((job / NBUF) & 1) ^ 1u);
             float *S = bufs + (size_t)bf * BUF_FLOATS;
             const float reg = lambda * (float)(e - s);
+            // fp16-packed solver: the system goes out scaled by the power of two that brings its first diagonal entry into [1, 2)
+            // (matrix and right-hand side alike: x is unchanged).  Thread 120 owns diagonal block 0.
+            if (tid == 120) {
+                const uint32_t ex = (__float_as_uint(acc[0][0] + reg) >> 23) & 0x1ffu;
+                scale_slot[job & 1] = (ex >= 1u && ex <= 253u) ? __uint_as_float((254u - ex) << 23) : 1.f;
+            }
+            acc_sync();
+            const float sc = scale_slot[job & 1];
             {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
                     for (int j = 0; j < 8; j += 2) {
                         const int k = 8 * bi + i, c0 = 8 * bj + j;
-                        float v0 = -acc[i][j], v1 = -acc[i][j + 1];
-                        if (k == c0) v0 -= k < d ? reg : 1.f;          // padded diagonal = 1 keeps the factorisation defined
-                        if (k == c0 + 1) v1 -= k < d ? reg : 1.f;
+                        float v0 = -acc[i][j] * sc, v1 = -acc[i][j + 1] * sc;
+                        if (k == c0) v0 -= k < d ? reg * sc : 1.f;     // padded diagonal = 1 keeps the factorisation defined
+                        if (k == c0 + 1) v1 -= k < d ? reg * sc : 1.f;
                         *reinterpret_cast<float2 *>(S + tile_at(k, c0)) = make_float2(v0, v1);
                     }
                 // the block right of the diagonal inside a diagonal 16 x 16 tile pair (rows 16 I .. +7, columns 16 I + 8 .. +15) is
@@ -187,20 +196,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_als_rows_wide(const int64_t *__r
                     for (int j = 0; j < 8; ++j)
 #pragma unroll
                         for (int i = 0; i < 8; i += 2)
-                            *reinterpret_cast<float2 *>(S + tile_at(8 * bj + j, 8 * bi + i)) = make_float2(-acc[i][j], -acc[i + 1][j]);
+                            *reinterpret_cast<float2 *>(S + tile_at(8 * bj + j, 8 * bi + i)) = make_float2(-acc[i][j] * sc, -acc[i + 1][j] * sc);
                 }
                 if (has_diag) {                                        // row bj of diagonal block bi
                     const int k = 8 * bi + bj;
 #pragma unroll
                     for (int j = 0; j < 8; j += 2) {
-                        float v0 = -dacc[j], v1 = -dacc[j + 1];
-                        if (bj == j) v0 -= k < d ? reg : 1.f;
-                        if (bj == j + 1) v1 -= k < d ? reg : 1.f;
+                        float v0 = -dacc[j] * sc, v1 = -dacc[j + 1] * sc;
+                        if (bj == j) v0 -= k < d ? reg * sc : 1.f;
+                        if (bj == j + 1) v1 -= k < d ? reg * sc : 1.f;
                         *reinterpret_cast<float2 *>(S + tile_at(k, 8 * bi + j)) = make_float2(v0, v1);
                     }
                 }
             }
-            S[TL::FLOATS + tid] = -bacc;
+            S[TL::FLOATS + tid] = -bacc * sc;
             acc_sync();
             if (tid == 0) mbar_arrive(bar_full(bf));
         }
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_als_rows_wide(const int64_t *__r
             float *bz = S + TL::FLOATS, *scratch = bz + DP, *xs = scratch + DP;
             mbar_wait(bar_full(bf), (uint32_t)((job / NBUF) & 1));
             float x[MT / 2];
-            cm::solve_tiles<MT>(S, bz, scratch, xs, lane, x);
+            cm::solve_tiles_h<MT>(S, bz, scratch, xs, lane, x);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty(bf));
             bool bad = false;

@@ -22,15 +22,14 @@
 //   2. "trsm" as a product: L(I, J) = S(I, J) (-W)^T for every m-tile of the panel (3 HMMA each);
 //   3. trailing update S(I, j) += L(I, J) L(j, J)^T for j > J (3 HMMA per tile, fragments straight from step 2);
 //   4. the same two steps for the right-hand-side row.
-// Back substitution runs on the same path: (1 x 8)(8 x 8) products, panels descending (see below).
+// Back substitution is scalar: one column per lane and 32-column block, panel-wise x_J = W_J^T r_J.  (A variant on the HMMA path
+// -- (1 x 8)(8 x 8) products, B fragments read transposed from the tiles -- cut the shared-memory wavefronts by 29 % and won 6 %
+// stand-alone, but lost 3 % inside the ALS kernel, where the tensor datapath is shared with tcgen05: profiles/r02_backsub_variants.txt.)
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #ifndef FMS_CHOL_F16
 #define FMS_CHOL_F16 1          // rank-64 kernel: 1 = fp16-packed HMMA.16816 products on a power-of-two scaled system, 0 = 3xTF32
-#endif
-#ifndef FMS_CHOL_BACKSUB
-#define FMS_CHOL_BACKSUB 0     // 0 scalar, 1 tensor path (NT accumulators), 2 tensor path in two phases (NT / 2 accumulators)
 #endif
 #include <stdint.h>
 
@@ -243,7 +242,6 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
         __syncwarp();
     }
 
-#if FMS_CHOL_BACKSUB == 0
     // ---- back substitution L^T x = z: column i = lane + 32 q per lane, one panel (8 pivots) at a time, blocks of 32 columns
     // descending.  x_J = W_J^T r_J with W_J = Ld^-1 stored over the diagonal block: no sequential triangular solve.
     constexpr int NQ = MT / 2;
@@ -301,117 +299,6 @@ __device__ __forceinline__ void solve_tiles(float *__restrict__ S, float *__rest
             }
         }
     }
-#elif FMS_CHOL_BACKSUB == 1
-    // ---- back substitution L^T x = z, on the tensor path as well.  Row-vector form, panels descending:
-    //          x_P = r_P W_P      (W_P = Ld^-1 sits where the diagonal block was: x_P[c] = sum_r r_P[r] W[r][c])
-    //          r_j -= x_P L(P, j) for j < P
-    // Each is a (1 x 8)(8 x 8) product: the vector is row 0 of the A operand, B[k][n] = T[8 P + k][8 j + pi(n)] is read straight
-    // from the tile layout (two LDS.32 per lane, 2-way bank conflict; the scalar version cost 4x the shared-memory wavefronts).
-    // pi(n) = n / 2 + 4 (n % 2): the accumulator of one product (lane (0, t): n = 2t, 2t + 1 -> columns t, t + 4) then IS the
-    // A fragment of the next (k slots t, t + 4).  All 8 row groups g carry the same vector (harmless, and no lane is special).
-    float4 rc[NT];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) rc[j] = make_float4(bz[8 * j + t], bz[8 * j + t + 4], 0.f, 0.f);
-    const int colp = (g >> 1) + 4 * (g & 1);
-    const float *Tb = S + 16 * t + 4 * (colp >> 1) + (colp & 1);
-#pragma unroll
-    for (int P = NT - 1; P >= 0; --P) {
-        const int I = P >> 1, hh = P & 1;
-        const float *Tp = Tb + (I * (I + 1)) * 128 + 2 * hh;             // tile (I, j) at + 128 j; k slot t + 4 at + 64
-        AFrag af;
-        af.h1 = af.h3 = af.l1 = af.l3 = 0u;
-        uint32_t h0, l0, h1, l1;
-        split_tf32(Tp[128 * P], h0, l0);
-        split_tf32(Tp[128 * P + 64], h1, l1);
-        split_tf32(rc[P].x, af.h0, af.l0);
-        split_tf32(rc[P].y, af.h2, af.l2);
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        mma3(x, af, bfrag(h0, h1), bfrag(l0, l1));
-        if (g == 0) { xs[8 * P + t] = x.x; xs[8 * P + t + 4] = x.y; }
-        split_tf32(-x.x, af.h0, af.l0);
-        split_tf32(-x.y, af.h2, af.l2);
-#pragma unroll
-        for (int j = 0; j < P; ++j) {
-            split_tf32(Tp[128 * j], h0, l0);
-            split_tf32(Tp[128 * j + 64], h1, l1);
-            mma3(rc[j], af, bfrag(h0, h1), bfrag(l0, l1));
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < MT / 2; ++q) x_out[q] = xs[lane + 32 * q];
-#else
-    // Same products as variant 1, ordered so that only NT / 2 accumulators are live: panels NT-1 .. NT/2 first (updating the
-    // upper half of r only), then their x re-read from xs for the lower half of r, then panels NT/2-1 .. 0.
-    constexpr int NH = NT / 2;
-    const int colp = (g >> 1) + 4 * (g & 1);
-    const float *Tb = S + 16 * t + 4 * (colp >> 1) + (colp & 1);
-    float4 rc[NH];
-    AFrag af;
-    af.h1 = af.h3 = af.l1 = af.l3 = 0u;
-    uint32_t h0, l0, h1, l1;
-#pragma unroll
-    for (int j = 0; j < NH; ++j) rc[j] = make_float4(bz[8 * (NH + j) + t], bz[8 * (NH + j) + t + 4], 0.f, 0.f);
-#pragma unroll
-    for (int P = NT - 1; P >= NH; --P) {
-        const int I = P >> 1, hh = P & 1;
-        const float *Tp = Tb + (I * (I + 1)) * 128 + 2 * hh;
-        split_tf32(Tp[128 * P], h0, l0);
-        split_tf32(Tp[128 * P + 64], h1, l1);
-        split_tf32(rc[P - NH].x, af.h0, af.l0);
-        split_tf32(rc[P - NH].y, af.h2, af.l2);
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        mma3(x, af, bfrag(h0, h1), bfrag(l0, l1));
-        if (g == 0) { xs[8 * P + t] = x.x; xs[8 * P + t + 4] = x.y; }
-        split_tf32(-x.x, af.h0, af.l0);
-        split_tf32(-x.y, af.h2, af.l2);
-#pragma unroll
-        for (int j = NH; j < P; ++j) {
-            split_tf32(Tp[128 * j], h0, l0);
-            split_tf32(Tp[128 * j + 64], h1, l1);
-            mma3(rc[j - NH], af, bfrag(h0, h1), bfrag(l0, l1));
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < NH; ++j) rc[j] = make_float4(bz[8 * j + t], bz[8 * j + t + 4], 0.f, 0.f);
-#pragma unroll
-    for (int P = NT - 1; P >= NH; --P) {
-        const int I = P >> 1, hh = P & 1;
-        const float *Tp = Tb + (I * (I + 1)) * 128 + 2 * hh;
-        split_tf32(-xs[8 * P + t], af.h0, af.l0);
-        split_tf32(-xs[8 * P + t + 4], af.h2, af.l2);
-#pragma unroll
-        for (int j = 0; j < NH; ++j) {
-            split_tf32(Tp[128 * j], h0, l0);
-            split_tf32(Tp[128 * j + 64], h1, l1);
-            mma3(rc[j], af, bfrag(h0, h1), bfrag(l0, l1));
-        }
-    }
-#pragma unroll
-    for (int P = NH - 1; P >= 0; --P) {
-        const int I = P >> 1, hh = P & 1;
-        const float *Tp = Tb + (I * (I + 1)) * 128 + 2 * hh;
-        split_tf32(Tp[128 * P], h0, l0);
-        split_tf32(Tp[128 * P + 64], h1, l1);
-        split_tf32(rc[P].x, af.h0, af.l0);
-        split_tf32(rc[P].y, af.h2, af.l2);
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        mma3(x, af, bfrag(h0, h1), bfrag(l0, l1));
-        if (g == 0) { xs[8 * P + t] = x.x; xs[8 * P + t + 4] = x.y; }
-        split_tf32(-x.x, af.h0, af.l0);
-        split_tf32(-x.y, af.h2, af.l2);
-#pragma unroll
-        for (int j = 0; j < P; ++j) {
-            split_tf32(Tp[128 * j], h0, l0);
-            split_tf32(Tp[128 * j + 64], h1, l1);
-            mma3(rc[j], af, bfrag(h0, h1), bfrag(l0, l1));
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < MT / 2; ++q) x_out[q] = xs[lane + 32 * q];
-#endif
 }
 
 // ---- fp16-packed products (m16n8k16): see solve_tiles_h
@@ -432,18 +319,27 @@ __device__ __forceinline__ void mma_f16(float4 &c, uint32_t a0, uint32_t a1, uin
         : "+f"(c.x), "+f"(c.y), "+f"(c.z), "+f"(c.w)
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "l"(b));
 }
-// A operand from an accumulator-layout tile, hi and lo halves as f16x2: h0 / l0 = (row g, cols 2t, 2t+1), h1 / l1 = (row g + 8, ...)
+// A operand from an accumulator-layout tile, hi and lo halves as f16x2: h0 / l0 = (row g, cols 2t, 2t+1), h1 / l1 = (row g + 8, ...).
+// The instruction wants the operand in four consecutive registers [a | a]: the duplicates are made ONCE per tile (opaque movs, so
+// ptxas keeps the quad instead of rebuilding it with two MOVs in front of every HMMA).
+__device__ __forceinline__ uint32_t dup32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
 struct AFragH {
-    uint32_t h0, h1, l0, l1;
+    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
     __device__ __forceinline__ void set(float x, float y, float z, float w) {
         split_h2(x, y, h0, l0);
         split_h2(z, w, h1, l1);
+        dup();
     }
+    __device__ __forceinline__ void dup() { h2 = dup32(h0); h3 = dup32(h1); l2 = dup32(l0); l3 = dup32(l1); }
 };
 // c += A B^T, B = {hi, lo} packed along K: a_lo (b_hi + b_lo), then a_hi (b_hi + b_lo)
 __device__ __forceinline__ void mma2h(float4 &c, const AFragH &a, BFrag b) {
-    mma_f16(c, a.l0, a.l1, a.l0, a.l1, b);
-    mma_f16(c, a.h0, a.h1, a.h0, a.h1, b);
+    mma_f16(c, a.l0, a.l1, a.l2, a.l3, b);
+    mma_f16(c, a.h0, a.h1, a.h2, a.h3, b);
 }
 
 // fp16-packed variant of solve_tiles (FMS_CHOL_F16 = 1): every product runs as TWO HMMA.16816.F32 with the hi and the lo parts
@@ -539,10 +435,10 @@ __device__ __forceinline__ void solve_tiles_h(float *__restrict__ S, float *__re
                     float4 c0 = S4[(I * (I + 1) + j) * 32 + lane];
                     float4 c1 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (two) c1 = S4[(I * (I + 1) + j - 1) * 32 + lane];
-                    mma_f16(c0, af.l0, af.l1, af.l0, af.l1, bf[j]);
-                    mma_f16(c1, af.l0, af.l1, af.l0, af.l1, bf[j - 1]);
-                    mma_f16(c0, af.h0, af.h1, af.h0, af.h1, bf[j]);
-                    mma_f16(c1, af.h0, af.h1, af.h0, af.h1, bf[j - 1]);
+                    mma_f16(c0, af.l0, af.l1, af.l2, af.l3, bf[j]);
+                    mma_f16(c1, af.l0, af.l1, af.l2, af.l3, bf[j - 1]);
+                    mma_f16(c0, af.h0, af.h1, af.h2, af.h3, bf[j]);
+                    mma_f16(c1, af.h0, af.h1, af.h2, af.h3, bf[j - 1]);
                     S4[(I * (I + 1) + j) * 32 + lane] = c0;
                     if (two) S4[(I * (I + 1) + j - 1) * 32 + lane] = c1;
                 }
@@ -558,10 +454,12 @@ __device__ __forceinline__ void solve_tiles_h(float *__restrict__ S, float *__re
             AFragH af;
             af.h1 = af.l1 = 0u;
             split_h2(bv.x, bv.y, af.h0, af.l0);
+            af.dup();
             float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             mma2h(z, af, wb);
             if (g == 0) *reinterpret_cast<float2 *>(bz + 8 * J + 2 * t) = make_float2(z.x, z.y);
             split_h2(z.x, z.y, af.h0, af.l0);
+            af.dup();
             // descending pairs like the trailing update (two independent 3-HMMA chains per branch)
 #pragma unroll
             for (int j = NT - 1; j >= 1; j -= 2) {
@@ -573,10 +471,10 @@ __device__ __forceinline__ void solve_tiles_h(float *__restrict__ S, float *__re
                     if (two) cv1 = *reinterpret_cast<const float2 *>(bz + 8 * j - 8 + 2 * t);
                 }
                 float4 c0 = make_float4(cv0.x, cv0.y, 0.f, 0.f), c1 = make_float4(cv1.x, cv1.y, 0.f, 0.f);
-                mma_f16(c0, af.l0, af.l1, af.l0, af.l1, bf[j]);
-                mma_f16(c1, af.l0, af.l1, af.l0, af.l1, bf[j - 1]);
-                mma_f16(c0, af.h0, af.h1, af.h0, af.h1, bf[j]);
-                mma_f16(c1, af.h0, af.h1, af.h0, af.h1, bf[j - 1]);
+                mma_f16(c0, af.l0, af.l1, af.l2, af.l3, bf[j]);
+                mma_f16(c1, af.l0, af.l1, af.l2, af.l3, bf[j - 1]);
+                mma_f16(c0, af.h0, af.h1, af.h2, af.h3, bf[j]);
+                mma_f16(c1, af.h0, af.h1, af.h2, af.h3, bf[j - 1]);
                 if (g == 0) {
                     *reinterpret_cast<float2 *>(bz + 8 * j + 2 * t) = make_float2(c0.x, c0.y);
                     if (two) *reinterpret_cast<float2 *>(bz + 8 * j - 8 + 2 * t) = make_float2(c1.x, c1.y);
