@@ -218,8 +218,8 @@ struct Smem2 {
     static constexpr int bars = bufs + NSA * V2_BUF_FLOATS * 4;
     static constexpr int n_bars = 2 * NSTG_ + 2 * NACC + 2 * NSA;
     static constexpr int tmem_ptr = bars + n_bars * 8;
-    static constexpr int scale = tmem_ptr + 8;                 // two floats: power-of-two scale of the system being unpacked
-    static constexpr int total = tmem_ptr + 16;
+    static constexpr int scale = tmem_ptr + 16;                // 2 x 3 floats: power-of-two scales of the system being unpacked
+    static constexpr int total = tmem_ptr + 48;
 };
 
 __device__ __forceinline__ void tc_ld16x256_x4(uint32_t taddr, float (&v)[16]) {
@@ -424,23 +424,37 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
             mbar_wait(bar_acc_full(acc), (job / NACC) & 1);
             tc_fence_after();
             mbar_wait(bar_g_empty(g), ((job / NSA) & 1) ^ 1);
-            // fp16-packed solver (cm::solve_tiles_h): the system goes out scaled by the power of two that brings its first diagonal
-            // entry into [1, 2) -- matrix and right-hand side alike, so x is unchanged.  Warp 0 owns that entry; one named barrier
-            // among the four epilogue warps per system hands the factor over (two slots: a slow warp still reads the previous one).
-            float sc = 1.f;
+            // fp16-packed solver (cm::solve_tiles_h): the matrix goes out scaled by the power of two that brings its first diagonal
+            // entry into [1, 2); the right-hand side by that and a second power of two that brings its own magnitude to ~8 (x is
+            // linear in b: the solver multiplies the inverse back in) -- an fp16 lo part resolves 6e-8 ABSOLUTE, so both operands
+            // must sit near 1.  Warp 0 owns the entries; one named barrier among the four epilogue warps per system hands the
+            // factors over (two slot sets: a slow warp still reads the previous one).
+            float sc = 1.f, sb = 1.f;
             if (FMS_CHOL_F16 && !DUMP) {
                 if (q == 0) {
-                    float e1[4], e2[4];
+                    float e1[4], e2[4], eb[4];
                     tc_ld16x256_x1(tmem_base + (uint32_t)acc * ACC_COLS, e1);
                     tc_ld16x256_x1(tmem_base + (uint32_t)acc * ACC_COLS + 64, e2);
+                    tc_ld16x256_x1(tmem_base + (uint32_t)acc * ACC_COLS + 128, eb);
                     tc_wait_ld();
+                    // largest |b| among the first 16 components (the lanes t = 0 of this warp hold them)
+                    float m = t4 == 0 ? fmaxf(fabsf(fmaf(eb[1], LO_INV, eb[0])), fabsf(fmaf(eb[3], LO_INV, eb[2]))) : 0.f;
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
                     if (lane == 0) {
                         const uint32_t ex = (__float_as_uint(fmaf(LO_INV, e2[0], e1[0]) + reg) >> 23) & 0x1ffu;      // sign + exponent
-                        scale_slot[job & 1] = (ex >= 1u && ex <= 253u) ? __uint_as_float((254u - ex) << 23) : 1.f;   // positive, normal
+                        const float s_a = (ex >= 1u && ex <= 253u) ? __uint_as_float((254u - ex) << 23) : 1.f;       // first diagonal entry -> [1, 2)
+                        const uint32_t eb_ = (__float_as_uint(m * s_a) >> 23) & 0xffu;
+                        const bool okb = eb_ >= 8u && eb_ <= 250u;
+                        scale_slot[3 * (job & 1) + 0] = s_a;
+                        scale_slot[3 * (job & 1) + 1] = okb ? __uint_as_float((257u - eb_) << 23) : 1.f;             // largest of those |b| -> [8, 16)
+                        scale_slot[3 * (job & 1) + 2] = okb ? __uint_as_float((eb_ - 3u) << 23) : 1.f;               // its inverse, for x
                     }
                 }
                 asm volatile("bar.sync 2, 128;" ::: "memory");
-                sc = scale_slot[job & 1];
+                sc = scale_slot[3 * (job & 1)];
+                sb = sc * scale_slot[3 * (job & 1) + 1];
             }
             float *buf = reinterpret_cast<float *>(sm + SM::bufs) + (size_t)g * V2_BUF_FLOATS;
             float4 *tiles = reinterpret_cast<float4 *>(buf) + (q * (q + 1)) * 32 + lane;       // tile (q, j) at + 32 j
@@ -473,8 +487,9 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
             tc_wait_ld();
             if (t4 == 0) {
                 float *bz = buf + TL4::FLOATS;
-                bz[16 * q + g8] = -fmaf(bb[1], LO_INV, bb[0]) * sc;
-                bz[16 * q + g8 + 8] = -fmaf(bb[3], LO_INV, bb[2]) * sc;
+                bz[16 * q + g8] = -fmaf(bb[1], LO_INV, bb[0]) * sb;
+                bz[16 * q + g8 + 8] = -fmaf(bb[3], LO_INV, bb[2]) * sb;
+                if (q == 0 && g8 == 0 && FMS_CHOL_F16 && !DUMP) bz[D] = scale_slot[3 * (job & 1) + 2];   // 1 / (rhs-only scale), first scratch word
             }
             tc_fence_before();
             __syncwarp();
@@ -506,8 +521,13 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
                 }
                 float x[2] = {0.f, 0.f};
                 if (!(dbg & 16)) {
-                    if (FMS_CHOL_F16 && !DUMP) cm::solve_tiles_h<4>(S, bz, invd, xs, lane, x);
-                    else cm::solve_tiles<4>(S, bz, invd, xs, lane, x);
+                    if (FMS_CHOL_F16 && !DUMP) {
+                        const float inv_sb = invd[0];
+                        cm::solve_tiles_h<4>(S, bz, invd, xs, lane, x);
+                        x[0] *= inv_sb; x[1] *= inv_sb;
+                    } else {
+                        cm::solve_tiles<4>(S, bz, invd, xs, lane, x);
+                    }
                 }
                 const float b0 = x[0], b1 = x[1];
                 __half h0, l0, h1, l1;

@@ -25,7 +25,7 @@ using TL = cm::Tiles<MT>;
 constexpr int BUF_FLOATS = TL::FLOATS + 3 * DP;                              // tiles | bz | scratch | xs
 constexpr int STAGE_FLOATS = CH * DP + CH;                                   // CH partner rows | CH ratings
 constexpr int N_BARS = 2 * NST + 2 * NBUF;
-constexpr size_t SMEM_BYTES = (size_t)(NST * STAGE_FLOATS + NBUF * BUF_FLOATS) * 4 + N_BARS * 8 + 16;     // + scale slots
+constexpr size_t SMEM_BYTES = (size_t)(NST * STAGE_FLOATS + NBUF * BUF_FLOATS) * 4 + N_BARS * 8 + 32;     // + scale slots (2 x 3 floats)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -170,14 +170,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_als_rows_wide(const int64_t *__r
             mbar_wait(bar_empty(bf), (uint32_t)((job / NBUF) & 1) ^ 1u);
             float *S = bufs + (size_t)bf * BUF_FLOATS;
             const float reg = lambda * (float)(e - s);
-            // fp16-packed solver: the system goes out scaled by the power of two that brings its first diagonal entry into [1, 2)
-            // (matrix and right-hand side alike: x is unchanged).  Thread 120 owns diagonal block 0.
+            // fp16-packed solver: the matrix goes out scaled by the power of two that brings its first diagonal entry into [1, 2)
+            // (thread 120 owns diagonal block 0), the right-hand side by that and by a power of two of its own (below).
             if (tid == 120) {
                 const uint32_t ex = (__float_as_uint(acc[0][0] + reg) >> 23) & 0x1ffu;
-                scale_slot[job & 1] = (ex >= 1u && ex <= 253u) ? __uint_as_float((254u - ex) << 23) : 1.f;
+                scale_slot[3 * (job & 1)] = (ex >= 1u && ex <= 253u) ? __uint_as_float((254u - ex) << 23) : 1.f;
+            }
+            if (warp == 0) {                                            // largest |b| among the first 32 components
+                float m = fabsf(bacc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0) scale_slot[3 * (job & 1) + 1] = m;
             }
             acc_sync();
-            const float sc = scale_slot[job & 1];
+            const float sc = scale_slot[3 * (job & 1)];
+            float sb = sc, inv_sb = 1.f;
+            {
+                // the right-hand side gets a second power of two that brings its own magnitude to ~8 (an fp16 lo part resolves
+                // 6e-8 absolute); x is linear in b, the solver warp multiplies the inverse back in
+                const uint32_t eb_ = (__float_as_uint(scale_slot[3 * (job & 1) + 1] * sc) >> 23) & 0xffu;
+                if (eb_ >= 8u && eb_ <= 250u) { sb = sc * __uint_as_float((257u - eb_) << 23); inv_sb = __uint_as_float((eb_ - 3u) << 23); }
+            }
             {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -209,7 +222,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_als_rows_wide(const int64_t *__r
                     }
                 }
             }
-            S[TL::FLOATS + tid] = -bacc * sc;
+            S[TL::FLOATS + tid] = -bacc * sb;
+            if (tid == 0) S[TL::FLOATS + DP] = inv_sb;              // first scratch word: the solver multiplies x by it
             acc_sync();
             if (tid == 0) mbar_arrive(bar_full(bf));
         }
@@ -223,7 +237,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_als_rows_wide(const int64_t *__r
             float *bz = S + TL::FLOATS, *scratch = bz + DP, *xs = scratch + DP;
             mbar_wait(bar_full(bf), (uint32_t)((job / NBUF) & 1));
             float x[MT / 2];
+            const float inv_sb = scratch[0];
             cm::solve_tiles_h<MT>(S, bz, scratch, xs, lane, x);
+#pragma unroll
+            for (int q = 0; q < MT / 2; ++q) x[q] *= inv_sb;
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty(bf));
             bool bad = false;

@@ -397,3 +397,38 @@ def test_query_state_sees_online_sgd_updates(fms, ctx):
     assert after != before
     assert recs[0] == "1,U," + after[1]                     # the record the operator emitted is what the state now holds
     assert client.queryState("ALS_MODEL", "2-U") == ("2-U", "2.0;0.125")      # untouched row
+
+
+@pytest.mark.parametrize("scale,lam", [(1e-3, 0.9), (1.0, 1e-3), (300.0, 0.9), (1.0, 30.0)])
+def test_rank64_solver_scaling_over_rating_and_lambda_ranges(fms, ctx, scale, lam):
+    """The rank-64 solver multiplies fp16 hi/lo operands on a system scaled by powers of two (matrix by its first diagonal entry,
+    right-hand side by its own magnitude): ratings of very different size and regularisation from weak to dominant must stay
+    inside the half-step tolerance -- or, where the system is so ill-conditioned that fp32 itself cannot (lambda = 1e-3 with
+    fewer ratings than factors), within 3x of what the plain fp32 CUDA-core kernel reaches against the fp64 oracle."""
+    u, i, r = _case(fms, 400, 120, 9000, seed=77)
+    r = r * scale
+    errs = {}
+    for kernel in (fms._native.ALS_KERNEL_GENERIC, fms._native.ALS_KERNEL_AUTO):
+        orc = oracle.OracleALS(u, i, r)
+        ctx.als_set_kernel(kernel)
+        ctx.als_load(u, i, r)
+        ctx.als_init(64, 42)
+        _, Y0 = ctx.als_get_factors(fms._native.ITEMS)
+        orc.init(64, 42)
+        orc.set_factors(1, Y0)
+        ctx.als_half_step(fms._native.USERS, lam)
+        orc.half_step(0, lam)
+        _, X = ctx.als_get_factors(fms._native.USERS)
+        _, OX = orc.factors(0)
+        assert ctx.als_last_info() == 0
+        e_users = rel_err(X, OX)
+        orc.set_factors(0, X)
+        ctx.als_half_step(fms._native.ITEMS, lam)      # now the Gramian is built from the (scaled) user factors
+        orc.half_step(1, lam)
+        _, Y = ctx.als_get_factors(fms._native.ITEMS)
+        _, OY = orc.factors(1)
+        assert ctx.als_last_info() == 0
+        errs[kernel] = max(e_users, rel_err(Y, OY))
+    ctx.als_set_kernel(fms._native.ALS_KERNEL_AUTO)
+    bound = max(HALF_TOL, 3.0 * errs[fms._native.ALS_KERNEL_GENERIC])
+    assert errs[fms._native.ALS_KERNEL_AUTO] <= bound, errs
