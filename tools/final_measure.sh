@@ -14,4 +14,5 @@ timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"k_als_rows_tc64" -c 2 -f -o gpurun_out/${P}_als python bench.py --steps 1 --warmup 0 --skip-svm --skip-cpu --skip-e2e --skip-parity > gpurun_out/${P}_als_under_ncu.log 2>&1
 timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:"k_svm_sweep_warp" -c 1 -f -o gpurun_out/${P}_svm python tools/svm_probe.py 10000000 28416 > gpurun_out/${P}_svm_under_ncu.log 2>&1
 timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:"k_als_rows_wide" -c 2 -f -o gpurun_out/${P}_wide python bench.py --rank 128 --steps 1 --warmup 0 --skip-svm --skip-cpu --skip-e2e --skip-parity > gpurun_out/${P}_wide_under_ncu.log 2>&1
+(cd tools/micro && ./chol_mma_test 4 16 && ./chol_mma_test 4 16 h && ./chol_mma_test 8 4 h) > gpurun_out/${P}_solver_harness.txt 2>&1
 ls -la gpurun_out | tail -14
