@@ -286,8 +286,11 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
     }
     if (fs.wait_flags != nullptr && threadIdx.x == 0) {
         // every rank's rows of the side this half-step gathers from have landed in OUR replica (and every rank is done with it)
+        const long long t0 = clock64();
         for (int r = 0; r < fs.n; ++r)
-            while (ld_acquire_sys(fs.wait_flags + r) < fs.wait_epoch) {}
+            while (ld_acquire_sys(fs.wait_flags + r) < fs.wait_epoch) {
+                if (clock64() - t0 > 8000000000LL) { atomicAdd(info, 1 << 20); break; }      // ~4 s: a peer is gone; do not hang the GPU
+            }
     }
     fence_proxy_async();                                           // the zero fill must be visible to the tensor core
     tc_fence_before();

@@ -229,6 +229,10 @@ FMS_API int fms_als_last_info(fms_ctx *ctx, int64_t *bad_rows) {
     int h = 0;
     FMS_CUDA(ctx, cudaMemcpyAsync(&h, A.info.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     FMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h >= (1 << 20)) {       // set by a half-step whose in-kernel wait for a peer rank's epoch flag timed out (fms_als_planes_flag_sync)
+        if (bad_rows) *bad_rows = h & ((1 << 20) - 1);
+        return fail(ctx, FMS_ERR_STATE, "ALS half-step: a peer rank never published its epoch (in-kernel flag wait timed out)");
+    }
     if (bad_rows) *bad_rows = h;
     return FMS_OK;
 }

@@ -346,6 +346,7 @@ int svm_exchange_open(fms_ctx *ctx, const void *handles, int n_ranks, int my_ran
 int svm_launch_exchange_apply(fms_ctx *ctx) {
     SvmState &S = ctx->svm;
     if (S.xchg_n < 2) return fail(ctx, FMS_ERR_STATE, "fms_svm_round_exchange: fms_svm_exchange_open_peers first");
+    if (S.xchg_dim != S.dim) return fail(ctx, FMS_ERR_STATE, "fms_svm_round_exchange: the exchange buffers were set up for dim %d, the loaded problem has %d", S.xchg_dim, S.dim);
     ++S.xchg_epoch;
     k_svm_exchange_apply<<<1, 1024, 0, ctx->stream>>>(S.w.p, S.delta.p, reinterpret_cast<float *const *>(S.xchg_tab.p), S.xchg_n, S.xchg_rank, S.dim,
                                                        S.xchg_epoch, (float)(S.stepsize / (double)S.blocks), S.xchg_err.p);
