@@ -7,10 +7,10 @@
 // accumulator.  The ratings are pre-laid as 16-entry stages (rows padded with a zero plane row).
 //
 // 24 warps (role counts are template parameters of the kernel), register budgets set per role with setmaxnreg:
-//   producers (3-6): stream the stage layout; for long rows (every stage a DRAM gather) they issue TMA gather4 loads of the 16
-//                    partner rows (hi half and lo half of the plane row) straight into the UMMA MN-major / 128-byte-swizzle
-//                    stage -- no registers, no per-rating SM instructions; for short rows (plane rows in L2, their
-//                    instructions compete with the solvers) 16-byte LDGSTS copies.  The ratings go into two 16-byte column
+//   producers (3-6): stream the stage layout and bring the 16 partner rows of a stage (hi half and lo half of the plane row)
+//                    straight into the UMMA MN-major / 128-byte-swizzle stage, either by TMA gather4 from one elected lane (no
+//                    registers, few instructions: the default beside 16 busy solver warps, i.e. for short rows) or by 16-byte
+//                    LDGSTS copies (the default for long rows); results are bitwise equal.  The ratings go into two 16-byte column
 //                    groups R, R' of a third operand chunk.  A ring SLOT is KS stages of 16 ratings (6 KB each): one
 //                    mbarrier full / empty handshake per slot.
 //   MMA warp       : per stage two tcgen05.mma (kind::f16, M=64, K=16):
@@ -20,11 +20,13 @@
 //                    b = Y^T r.  Accumulators live in TMEM (2 slots x 256 columns).
 //   epilogue (4)   : tcgen05.ld.16x256b -- the register layout of an mma.sync accumulator -- one m-tile of 16 rows each;
 //                    -(D1 + 2^-11 D2 + lambda n I) goes out as 16x8 fragment tiles (chol_mma.cuh), -b as a vector, into
-//                    the shared-memory buffer of a solver warp
+//                    the shared-memory buffer of a solver warp -- both scaled by powers of two (matrix: first diagonal entry
+//                    -> [1, 2); right-hand side: its own magnitude -> ~8) so that fp16 hi/lo operands keep 22 bits
 //   solvers (12-16): one system per warp on the warp-level tensor path: blocked right-looking Cholesky, 8x8 diagonal
-//                    blocks factored redundantly in registers, triangular solves and trailing updates as 3xTF32 HMMA on
-//                    the fragment tiles, forward substitution as one more matrix row, panel-wise back substitution
-//                    (cm::solve_tiles); writes x (fp32) and its plane row -- into every rank's replica when peers are
+//                    blocks factored redundantly in registers, triangular solves and trailing updates as fp16-packed
+//                    HMMA.16816 products (hi and lo parts along K: 2 instructions per full-precision product) on the
+//                    fragment tiles, forward substitution as one more matrix row, panel-wise back substitution
+//                    (cm::solve_tiles_h); writes x (fp32) and its plane row -- into every rank's replica when peers are
 //                    mapped (NVLink stores).
 // Round 1's solver (one matrix row per lane, FFMA2 against broadcast LDS.128) ran the short-row half-step at 94 % of the
 // shared-memory data pipe; profiles/README.md has the numbers that led here.

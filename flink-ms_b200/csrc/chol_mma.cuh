@@ -1,5 +1,8 @@
-// chol_mma.cuh -- one warp solves one SPD system (A + lambda n I) x = b of order D = 16 MT on the warp-level tensor path
-// (mma.sync m16n8k8 TF32, SASS HMMA.1688.F32.TF32) with error-compensated 3xTF32 products.
+// chol_mma.cuh -- one warp solves one SPD system (A + lambda n I) x = b of order D = 16 MT on the warp-level tensor path.
+// Two product flavours with the same structure and the same accuracy (5e-6 worst case against an fp64 solve):
+//   solve_tiles    mma.sync m16n8k8 TF32 (SASS HMMA.1688.F32.TF32), error-compensated 3xTF32: 3 instructions per product;
+//   solve_tiles_h  mma.sync m16n8k16 f16 (SASS HMMA.16816.F32), hi and lo parts packed along K: 2 instructions per product,
+//                  B fragments half the size; the caller scales the system by powers of two.  The ALS kernels use this one.
 //
 // Why: the round-1 solver (one matrix row per lane, trailing updates as FFMA2 against broadcast LDS.128) was bound by the
 // shared-memory data pipe (ncu: l1tex data-pipe wavefronts 94 % of peak, 2 240 of them per 64x64 system) and by issue
