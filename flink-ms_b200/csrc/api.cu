@@ -876,8 +876,11 @@ FMS_API int fms_svm_stream_begin(fms_ctx *ctx, int64_t n_total, int32_t dim) {
     if (!ctx->members.empty()) {
         // a group scatters the rows over its members by block at fit time: stage them in host memory inside the library
         auto &T = ctx->staged;
-        try { T.hX.clear(); T.hX.reserve((size_t)n_total * (size_t)dim); } catch (const std::bad_alloc &) { return fail(ctx, FMS_ERR_OOM, "fms_svm_stream_begin: host staging of %lld x %d floats", (long long)n_total, dim); }
-        T.y.clear(); T.bid.clear();
+        try {
+            T.hX.clear(); T.y.clear(); T.bid.clear();
+            T.hX.reserve((size_t)n_total * (size_t)dim);          // reserved up front: the appends never allocate (no exception may cross the C-ABI)
+            T.y.reserve((size_t)n_total); T.bid.reserve((size_t)n_total);
+        } catch (const std::bad_alloc &) { return fail(ctx, FMS_ERR_OOM, "fms_svm_stream_begin: host staging of %lld x %d floats", (long long)n_total, dim); }
         T.n_cap = n_total; T.n_fill = 0; T.dim = dim;
         return FMS_OK;
     }
