@@ -887,8 +887,10 @@ FMS_API int fms_svm_stream_begin(fms_ctx *ctx, int64_t n_total, int32_t dim) {
     CHECK_CTX(ctx);
     auto &T = ctx->staged;
     FMS_CUDA(ctx, T.X.alloc((size_t)n_total * (size_t)dim));
-    T.y.clear(); T.bid.clear();
-    T.y.reserve((size_t)n_total); T.bid.reserve((size_t)n_total);
+    try {
+        T.y.clear(); T.bid.clear();
+        T.y.reserve((size_t)n_total); T.bid.reserve((size_t)n_total);
+    } catch (const std::bad_alloc &) { return fail(ctx, FMS_ERR_OOM, "fms_svm_stream_begin: host staging of %lld labels", (long long)n_total); }
     T.n_cap = n_total; T.n_fill = 0; T.dim = dim;
     return FMS_OK;
 }
