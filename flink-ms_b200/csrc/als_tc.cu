@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_als_rows_tc64(
                     for (int p = 0; p < n_peers; ++p) *reinterpret_cast<uint2 *>(peers[p] + poff) = prow;
                 }
                 // NaN / inf: the factorisation broke down; beyond +-65504 the fp16 gather planes cannot carry the value to the next
-                // half-step (the fp32 row in T is still exact): both are counted, fms_als_fit / fms_als_info report the count
+                // half-step (the fp32 row in T is still exact): both are counted, fms_als_fit / fms_als_last_info report the count
                 const bool bad = !(fabsf(b0) <= 65504.f) || !(fabsf(b1) <= 65504.f);
                 if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(info, 1);
             }
