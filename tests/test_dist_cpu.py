@@ -154,3 +154,56 @@ def test_shard_range_covers_rows_once():
                 covered.append((b, e))
             assert sum(e - b for b, e in covered) == n
             assert all(covered[k][1] == covered[k + 1][0] or covered[k + 1][0] == n for k in range(world - 1))
+
+
+class ExchangeSVMBackend(NumpySVMBackend):
+    """The fused exchange path of ContextSVMBackend restated on gloo: every rank's delta lands in slot [rank] of every rank's
+    buffer (all_gather), the slots are summed IN RANK ORDER and applied -- what k_svm_exchange_apply does over NVLink.  sweep /
+    delta_tensor / apply must not be called by DistributedSVM once p2p is on."""
+    p2p = True
+
+    def round_exchange(self, local_iterations):
+        NumpySVMBackend.sweep(self, local_iterations)
+        world = dist.get_world_size()
+        slots = [torch.zeros_like(self.delta) for _ in range(world)]
+        dist.all_gather(slots, self.delta)
+        s = torch.zeros_like(self.delta)
+        for r in range(world):
+            s += slots[r]
+        self.w = self.w + s.numpy() * (1.0 / self.K)
+
+    def sweep(self, local_iterations):
+        raise AssertionError("DistributedSVM.round must use round_exchange when the backend has p2p on")
+
+    def apply(self):
+        raise AssertionError("DistributedSVM.round must use round_exchange when the backend has p2p on")
+
+
+def _svm_exchange_worker(me, world, port, q):
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=me, world_size=world)
+    D = importlib.import_module("flink-ms_b200.dist")
+    synth = importlib.import_module("flink-ms_b200.synth")
+    X, y, _ = synth.svm_data(240, 12, seed=2)
+    bid = np.arange(240) % 4
+    dsvm = D.DistributedSVM(ExchangeSVMBackend(X, y, bid, 4, world, me, -1, 42))
+    dsvm.fit(3, -1)
+    q.put((me, dsvm.b.w))
+    dist.destroy_process_group()
+
+
+def test_sharded_svm_exchange_path_is_rank_ordered_and_identical_on_all_ranks():
+    import oracle
+    synth = importlib.import_module("flink-ms_b200.synth")
+    X, y, _ = synth.svm_data(240, 12, seed=2)
+    bid = np.arange(240) % 4
+    want = oracle.svm_fit(X, y, bid, 4, 3, -1, 1.0, 1.0, 42, 0)
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctxm.Process(target=_svm_exchange_worker, args=(g, 2, port, q)) for g in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=120) for _ in procs)
+    [p.join(60) for p in procs]
+    assert np.array_equal(res[0], res[1])                       # same summation order on every rank: the same bits
+    assert np.allclose(res[0], want, rtol=1e-12, atol=1e-14)
