@@ -64,3 +64,20 @@ def test_no_gpu_means_loud_failure(fms):
     assert lib.fms_create(None, None, 1) == fms._native.ERR_INVALID_ARG
     h = ctypes.c_void_p()
     assert lib.fms_create(ctypes.byref(h), None, 2) == fms._native.ERR_INVALID_ARG      # a group needs explicit device ids
+
+
+def test_jni_shim_type_checks_against_the_header_and_matches_native_java():
+    """No JDK in the build image: the JNI shim (flink-ms_b200/jvm/jni/flinkms_jni.c) is source-only.  It still must (a) type-check
+    against include/flinkms.h -- with a stand-in <jni.h> that declares just the JNI calls the shim uses -- and (b) implement
+    exactly the native methods Native.java declares."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = os.path.join(root, "flink-ms_b200", "jvm", "jni", "flinkms_jni.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(root, "tests", "jni_stub"), "-I",
+                        os.path.join(root, "include"), shim], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    c_names = sorted(set(re.findall(r"Java_de_tub_it4bi_gpu_Native_(\w+)", open(shim).read())))
+    java = open(os.path.join(root, "flink-ms_b200", "jvm", "src", "main", "java", "de", "tub", "it4bi", "gpu", "Native.java")).read()
+    j_names = sorted(set(re.findall(r"private static native [\w\[\]]+ (\w+)\(", java)))
+    assert c_names == j_names
