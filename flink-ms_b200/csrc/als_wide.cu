@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_als_rows_wide(const int64_t *__r
             mbar_wait(bar_full(bf), (uint32_t)((job / NBUF) & 1));
             float x[MT / 2];
             const float inv_sb = scratch[0];
-            cm::solve_tiles_h<MT>(S, bz, scratch, xs, lane, x);
+            cm::solve_tiles_h<MT, true>(S, bz, scratch, xs, lane, x);      // rolled row-tile loops: the solver must fit the 32 KB instruction cache
 #pragma unroll
             for (int q = 0; q < MT / 2; ++q) x[q] *= inv_sb;
             __syncwarp();

@@ -354,7 +354,7 @@ __device__ __forceinline__ void mma2h(float4 &c, const AFragH &a, BFrag b) {
 // invd: D floats scratch (unused by the solver since W replaces the diagonal blocks; kept for the caller's staging).  xs: D floats scratch (x, for the broadcasts of the back substitution).
 // x_out[q] = x[lane + 32 q].  All four arrays are private to the calling warp; the caller provides the barrier that
 // made S and bz visible (mbarrier wait or __syncwarp).
-template <int MT>
+template <int MT, bool ROLL = false>
 __device__ __forceinline__ void solve_tiles_h(float *__restrict__ S, float *__restrict__ bz, float *__restrict__ invd, float *__restrict__ xs,
                                             const int lane, float (&x_out)[MT / 2]) {
     using TL = Tiles<MT>;
@@ -409,6 +409,55 @@ __device__ __forceinline__ void solve_tiles_h(float *__restrict__ S, float *__re
             wb = bfrag(h0, l0);
         }
         // ---- 2 + 3. panel tiles: L(I, J) = S(I, J) (-W)^T, then S(I, j) += L(I, J) L(j, J)^T for J < j <= 2 I + 1
+        if constexpr (ROLL) {
+            // Code-size variant for MT = 8 (als_wide.cu): the unrolled form above is 25 KB of SASS per panel iteration, beyond the
+            // 32 KB instruction cache once ten warps run different parts of the kernel.  The row tiles are walked by two RUNTIME
+            // loops (tiles 0 .. MT/2-1, which only meet n-tiles 0 .. MT-1, and tiles MT/2 .. MT-1, which meet all of them); the
+            // B-fragment registers keep their static indices: the new pair is steered into bf[2 I], bf[2 I + 1] by a static
+            // select, the pair loop is unrolled over all candidates and guarded by uniform branches.
+            constexpr int HB = MT / 2;
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+#pragma unroll 1
+                for (int Ir = 0; Ir < HB; ++Ir) {
+                    const int I = hb * HB + Ir;
+                    if (I < Id) continue;
+                    const int row0 = I * (I + 1);
+                    const float4 sv = S4[(row0 + J) * 32 + lane];
+                    AFragH af;
+                    af.set(sv.x, sv.y, sv.z, sv.w);
+                    float4 L = make_float4(0.f, 0.f, 0.f, 0.f);
+                    mma2h(L, af, wb);
+                    if (I == Id) {
+                        const bool u0 = 2 * t > g, u1 = 2 * t + 1 > g;
+                        if (h == 0) { L.x = u0 ? 0.f : L.x; L.y = u1 ? 0.f : L.y; }
+                        else { L.x = 0.f; L.y = 0.f; L.z = u0 ? 0.f : L.z; L.w = u1 ? 0.f : L.w; }
+                    }
+                    S4[(row0 + J) * 32 + lane] = L;
+                    af.set(L.x, L.y, L.z, L.w);
+                    const BFrag n0 = bfrag(af.h0, af.l0), n1 = bfrag(af.h1, af.l1);
+#pragma unroll
+                    for (int k = 0; k < HB; ++k)
+                        if (Ir == k) { bf[2 * (hb * HB + k)] = n0; bf[2 * (hb * HB + k) + 1] = n1; }
+#pragma unroll
+                    for (int m = (hb + 1) * HB - 1; m >= 0; --m) {
+                        const int j = 2 * m + 1;
+                        if (m > I) continue;                                // n-tiles right of this row tile's diagonal
+                        if (j <= J) break;
+                        const bool two = j - 1 > J;
+                        float4 c0 = S4[(row0 + j) * 32 + lane];
+                        float4 c1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (two) c1 = S4[(row0 + j - 1) * 32 + lane];
+                        mma_f16(c0, af.l0, af.l1, af.l2, af.l3, bf[j]);
+                        mma_f16(c1, af.l0, af.l1, af.l2, af.l3, bf[j - 1]);
+                        mma_f16(c0, af.h0, af.h1, af.h2, af.h3, bf[j]);
+                        mma_f16(c1, af.h0, af.h1, af.h2, af.h3, bf[j - 1]);
+                        S4[(row0 + j) * 32 + lane] = c0;
+                        if (two) S4[(row0 + j - 1) * 32 + lane] = c1;
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for (int I = 0; I < MT; ++I) {
             if (I >= Id) {
@@ -446,6 +495,7 @@ __device__ __forceinline__ void solve_tiles_h(float *__restrict__ S, float *__re
                     if (two) S4[(I * (I + 1) + j - 1) * 32 + lane] = c1;
                 }
             }
+        }
         }
         // the diagonal block of the factor is only ever used through its inverse again (back substitution): keep W = Ld^-1 there.
         // Lane (g, t) owns exactly the two entries W[g][2t], W[g][2t+1] of its fragment position.

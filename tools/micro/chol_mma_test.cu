@@ -10,7 +10,7 @@
 
 using namespace fms::cm;
 
-template <int MT, bool H>
+template <int MT, bool H, bool R = false>
 __global__ void __launch_bounds__(512, 1) k_solve(const float *__restrict__ A, const float *__restrict__ b, int n_sys, int reps, float *__restrict__ X,
                                                   long long *cyc) {
     using TL = Tiles<MT>;
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(512, 1) k_solve(const float *__restrict__ A, c
             for (int q = 0; q < D / 32; ++q) bz[lane + 32 * q] = -b[(size_t)s * D + lane + 32 * q] * sc;
             __syncwarp();
             float x[MT / 2];
-            if (H) solve_tiles_h<MT>(S, bz, invd, xs, lane, x);
+            if (H) solve_tiles_h<MT, R>(S, bz, invd, xs, lane, x);
             else solve_tiles<MT>(S, bz, invd, xs, lane, x);
             for (int q = 0; q < MT / 2; ++q) X[(size_t)s * D + lane + 32 * q] = x[q];
             __syncwarp();
@@ -64,7 +64,7 @@ static void chol_solve64(std::vector<double> &a, std::vector<double> &b, int d) 
     for (int i = d - 1; i >= 0; --i) { double v = b[i]; for (int k = i + 1; k < d; ++k) v -= a[k * d + i] * b[k]; b[i] = v / a[i * d + i]; }
 }
 
-template <int MT, bool H>
+template <int MT, bool H, bool R = false>
 static int run(int only_warps) {
     constexpr int D = 16 * MT;
     const int n_sys = 2048;
@@ -101,15 +101,15 @@ static int run(int only_warps) {
     for (int warps : {4, 8, 12, 16}) {
         const size_t smem = per_warp * warps;
         if (smem > 227 * 1024 || (only_warps && warps != only_warps)) continue;
-        cudaFuncSetAttribute(k_solve<MT, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_solve<MT, H, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int reps = 16;
-        k_solve<MT, H><<<148, warps * 32, smem>>>(dA, db, n_sys, 1, dX, dc);
+        k_solve<MT, H, R><<<148, warps * 32, smem>>>(dA, db, n_sys, 1, dX, dc);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        k_solve<MT, H><<<148, warps * 32, smem>>>(dA, db, n_sys, reps, dX, dc);
+        k_solve<MT, H, R><<<148, warps * 32, smem>>>(dA, db, n_sys, reps, dX, dc);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0.f;
@@ -146,7 +146,8 @@ static int run(int only_warps) {
 int main(int argc, char **argv) {
     const int mt = argc > 1 ? atoi(argv[1]) : 4;
     const int only = argc > 2 ? atoi(argv[2]) : 0;
-    const bool h = argc > 3 && argv[3][0] == 'h';               // fp16-packed products (solve_tiles_h)
+    const bool h = argc > 3 && (argv[3][0] == 'h' || argv[3][0] == 'r');   // fp16-packed products (solve_tiles_h); 'r': rolled row-tile loops
+    if (argc > 3 && argv[3][0] == 'r') { printf("fp16-packed, rolled\n"); return mt == 8 ? run<8, true, true>(only) : run<4, true, true>(only); }
     if (h) printf("fp16-packed variant\n");
     if (mt == 4) return h ? run<4, true>(only) : run<4, false>(only);
     if (mt == 8) return h ? run<8, true>(only) : run<8, false>(only);
